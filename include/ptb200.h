@@ -1,0 +1,212 @@
+/* ptb200.h — C ABI of the B200-native radiance loop for maurock/small-pathtracer.
+ *
+ * The reference has no FFI: its "API" is the set of C++ types and the triple loop
+ * in one translation unit (reference src/smallpt.cpp).  This header is the single
+ * process/device boundary the new build introduces.  Every entry point cites the
+ * reference code it replaces (file:line relative to the reference repo root).
+ *
+ * Conventions: return 0 = OK, negative = error (see pt_status); no C++ exceptions
+ * cross this ABI; the caller owns all host arrays; the library copies on upload and
+ * owns all device memory; one host thread drives a context; pt_render is synchronous
+ * on return.  Clamp, gamma and the PPM writer stay on the host (src/smallpt.cpp:314-321,
+ * :548-551) so output bytes come from the reference's own formula.
+ *
+ * There is NO CPU fallback behind these symbols: every compute entry fails with
+ * PT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- POD mirrors */
+
+/* Vec, src/smallpt.cpp:24-62 (three doubles; positions, directions and RGB). */
+typedef struct pt_vec3 { double x, y, z; } pt_vec3;
+
+/* Refl_t, src/smallpt.cpp:72-74 (enum values 0,1,2). */
+enum { PT_DIFF = 0, PT_SPEC = 1, PT_REFR = 2 };
+
+/* Sphere, src/smallpt.cpp:223-228 — field order of :225-227. */
+typedef struct pt_sphere {
+    double  rad;
+    pt_vec3 p, e, c;
+    int     refl;
+    int     _pad;
+} pt_sphere;
+
+/* Plane kinds.  XZ/XY/YZ are the reference's Rectangle_xz (:92-124), Rectangle_xy
+ * (:137-167), Rectangle_yz (:180-210): bounded, axis aligned, NO epsilon, in-plane hit
+ * coordinates rounded through float.  TILTED is the README's "tilted planes"
+ * (README.md:19), absent from the reference source (parity unpinned): bounded
+ * parallelogram patch given by a point, a unit normal and two in-plane unit axes. */
+enum { PT_PLANE_XZ = 0, PT_PLANE_XY = 1, PT_PLANE_YZ = 2, PT_PLANE_TILTED = 3 };
+
+typedef struct pt_plane {
+    int     kind;          /* PT_PLANE_* */
+    int     refl;          /* PT_DIFF / PT_SPEC / PT_REFR */
+    /* axis-aligned kinds: constructor argument order of the reference classes:
+     *   XZ: a=x, b=z, k=y   (Rectangle_xz(x1,x2,z1,z2,y,...)   :97)
+     *   XY: a=x, b=y, k=z   (Rectangle_xy(x1,x2,y1,y2,z,...)   :142)
+     *   YZ: a=y, b=z, k=x   (Rectangle_yz(y1,y2,z1,z2,x,...)   :185) */
+    double  a1, a2, b1, b2, k;
+    /* tilted kind: hit = o + d*tau, tau = n.(p0-o)/(n.d);
+     * accept iff |(hit-p0).s| <= hs && |(hit-p0).t| <= ht && tau > eps (eps = 1e-4). */
+    pt_vec3 p0, n, s, t;
+    double  hs, ht;
+    pt_vec3 e, c;          /* emission, colour */
+} pt_plane;
+
+/* Camera members, src/smallpt.cpp:281-284 (filled by the host Camera ctor :262-275). */
+typedef struct pt_camera {
+    pt_vec3 origin, lower_left_corner, horizontal, vertical;
+} pt_camera;
+
+/* Light descriptor for PT_MODE_NEE_REF_RECT: replaces the literals of
+ * src/smallpt.cpp:365-367 (32, 36, 63, 36, 81.6), :467 (id 6) and :471 (1296). */
+typedef struct pt_light {
+    int    id;             /* scene object id of the light (reference: 6)            */
+    int    _pad;
+    double x0, xw;         /* x_l = x0 + xw*xi   (reference: 32, 36)                  */
+    double z0, zw;         /* z_l = z0 + zw*xi   (reference: 63, 36)                  */
+    double y;              /* sampled plane      (reference: 81.6)                    */
+    double area;           /* PDF area           (reference: 1296)                    */
+} pt_light;
+
+/* Scene = ordered object table (the reference's `Hitable *rect[NUMBER_OBJ]`, :287-311).
+ * Object id = position in `order`.  order[i] >= 0 selects planes[order[i]];
+ * order[i] < 0 selects spheres[~order[i]].  order == NULL means: all planes in array
+ * order, then all spheres in array order. */
+typedef struct pt_scene {
+    const pt_sphere *spheres; int n_spheres;
+    const pt_plane  *planes;  int n_planes;
+    const int       *order;
+    pt_camera        camera;
+    pt_light         light;
+} pt_scene;
+
+#define PT_MAX_OBJECTS 1024
+
+/* Integrators.  COS / UNI = src/smallpt.cpp:474-477 arm with the cosine (:337-348) or
+ * uniform (:351-360, weight 1 — no 2cos factor, as in the reference) sampler;
+ * NEE_REF_RECT = :464-473 (hard-wired rectangular light sampling, reference-faithful);
+ * NEE_CONE_SPHERE = solid-angle cone sampling toward every emissive sphere + shadow
+ * ray (north-star; not in the reference source — parity unpinned). */
+enum { PT_MODE_NEE_REF_RECT = 0, PT_MODE_COS = 1, PT_MODE_UNI = 2, PT_MODE_NEE_CONE_SPHERE = 3 };
+
+/* RNG / arithmetic engines.
+ * PT_ENGINE_FP32_PHILOX  : production wavefront path tracer, FP32, Philox4x32-10 keyed by
+ *                          (pixel, sample, bounce).
+ * PT_ENGINE_FP64_ERAND48 : validation mode — replays the reference's per-row erand48 Xi
+ *                          stream (src/smallpt.cpp:530, src/utilities.h:26-51), one thread
+ *                          per row, FP64, no FMA contraction. */
+enum { PT_ENGINE_FP32_PHILOX = 0, PT_ENGINE_FP64_ERAND48 = 1 };
+
+/* sin/cos used by random_scattering in the FP64 engine:
+ * PT_SINCOS_LIBM = CUDA libm sin/cos (last-bit differences vs glibc are possible),
+ * PT_SINCOS_DET  = the deterministic +,-,*,/-only sincos of include/ptb200_detmath.h,
+ *                  bit-identical on host and device (oracle patch P6). */
+enum { PT_SINCOS_LIBM = 0, PT_SINCOS_DET = 1 };
+
+typedef struct pt_render_params {
+    int      width, height;   /* src/smallpt.cpp:507 */
+    int      spp;             /* src/smallpt.cpp:508 (`samps`) */
+    int      mode;            /* PT_MODE_* */
+    int      engine;          /* PT_ENGINE_* */
+    int      sincos;          /* PT_SINCOS_* (FP64 engine only) */
+    uint64_t seed;            /* Philox key (FP32 engine only) */
+    /* Row-tile sharding: tile k (tile_rows rows) belongs to rank k % world.
+     * rank=0, world=1 renders the whole image.  Pixels of foreign tiles stay zero. */
+    int      tile_rows;       /* 0 = default (8) */
+    int      rank, world;
+    int      max_depth;       /* safety cap on path length; 0 = default (4096) */
+    int      queue_capacity;  /* wavefront queue slots; 0 = default (sized to L2) */
+    int      collect_stats;   /* 1 = also accumulate per-pixel sum of squares */
+    int      _pad;
+} pt_render_params;
+
+typedef struct pt_stats {
+    uint64_t paths;             /* (pixel, sample) camera paths traced by this context   */
+    uint64_t rays_camera;       /* unique closest-hit queries by kind                    */
+    uint64_t rays_scatter;
+    uint64_t rays_shadow;
+    uint64_t shaded_vertices;   /* surface interactions shaded (bounces)                 */
+    uint64_t miss_events;       /* closest-hit queries that missed every object          */
+    uint64_t truncated;         /* paths cut by max_depth                                */
+    uint64_t kernel_launches;   /* CUDA kernels launched by the last pt_render           */
+    uint64_t iterations;        /* wavefront iterations of the last pt_render            */
+    uint32_t max_depth_seen;
+    uint32_t _pad;
+    double   render_ms;         /* device time of the last pt_render (CUDA events)       */
+    double   main_kernel_ms;    /* summed device time of the dominant kernel             */
+} pt_stats;
+
+typedef enum pt_status {
+    PT_OK = 0,
+    PT_ERR_ARG = -1,
+    PT_ERR_NO_DEVICE = -2,
+    PT_ERR_CUDA = -3,
+    PT_ERR_OOM = -4,
+    PT_ERR_STATE = -5
+} pt_status;
+
+typedef struct pt_ctx pt_ctx;
+
+/* ---------------------------------------------------------------- entry points */
+
+/* Create a context on the current CUDA device (or `device` >= 0) and upload the scene
+ * table + camera.  Replaces the global scene literal and Camera construction feeding the
+ * loop, src/smallpt.cpp:287-311 and :521. */
+int pt_scene_upload(pt_ctx **ctx, const pt_scene *scene, int device);
+
+/* Render: the whole triple loop rows x pixels x samples, src/smallpt.cpp:528-541, including
+ * radiance() (:419-496 with the dead RL block :424-442 removed) and everything below it.
+ * Accumulates into the context's device accumulation buffers (zeroed first). */
+int pt_render(pt_ctx *ctx, const pt_render_params *params);
+
+/* Same, but accumulate into caller-owned DEVICE memory (w*h*3 doubles, row-major, top row
+ * first, zeroed by the call) so a host runtime (torch.distributed) can gather row tiles
+ * with NCCL without a copy.  `stream` is a cudaStream_t (0 = the context's own stream). */
+int pt_render_into(pt_ctx *ctx, const pt_render_params *params, void *dev_rgb_sum, void *stream);
+
+/* Read back per-pixel UNCLAMPED mean radiance: rgb_mean[w*h*3] doubles, row-major, top row
+ * first (the order of `c[i]`, src/smallpt.cpp:538).  The caller applies clamp (:538) and
+ * toInt (:319-321).  rgb_sumsq (optional, may be NULL) receives per-pixel per-channel sums
+ * of squared sample radiance when collect_stats was set.  stats may be NULL. */
+int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats);
+
+/* Device pointer of the context-owned accumulation buffer (w*h*3 doubles: per-pixel SUM of
+ * sample radiance) of the last pt_render, for zero-copy gathers. */
+void *pt_accum_device_ptr(pt_ctx *ctx);
+
+/* Closest-hit query for unit tests — `intersect(Ray,t,id)`, src/smallpt.cpp:323-335, plus
+ * hittingPoint's miss rule (:371-377).  rays_od = n*6 doubles (o.xyz, d.xyz; d must be
+ * unit).  precision: 64 = FP64 reference-compat arithmetic, 32 = the FP32 production
+ * intersector.  t_out[i] = 1e20 and id_out[i] = -1 on a miss. */
+int pt_debug_intersect(pt_ctx *ctx, const double *rays_od, int n, int precision,
+                       double *t_out, int *id_out);
+
+/* Run `n_threads` independent erand48 streams (src/utilities.h:45-51) on the device:
+ * seeds = n_threads*3 uint16, out = n_threads*draws doubles. KAT entry. */
+int pt_debug_erand48(pt_ctx *ctx, const uint16_t *seeds, int n_threads, int draws, double *out);
+
+/* Philox4x32-10 on the device: ctr = n*4 uint32, key = n*2 uint32, out = n*4 uint32. KAT entry. */
+int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out);
+
+/* FFMA-only microbenchmark: measured FP32 issue peak of this device in TFLOP/s
+ * (FMA = 2 FLOPs), the denominator of the FP32 roofline. */
+int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
+
+void        pt_destroy(pt_ctx *ctx);
+const char *pt_last_error(pt_ctx *ctx);   /* ctx may be NULL: last error of a failed upload */
+const char *pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */
