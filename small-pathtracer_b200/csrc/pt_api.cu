@@ -1,0 +1,355 @@
+// pt_api.cu — the extern "C" boundary of libptb200.so (include/ptb200.h): context, scene upload,
+// render dispatch, readback, debug entries.  No torch types, plain pointers and sizes.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "pt_internal.h"
+
+static thread_local std::string g_last_error;   // for failures before a context exists
+
+int pt_fail(pt_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+static inline bool finite3(const pt_vec3 &v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); }
+
+// Build the FP32 class-sorted constant-memory image of the scene.
+static void build_scene_f32(pt_ctx *ctx)
+{
+    SceneF32 &S = *ctx->h_scene32;
+    std::memset(&S, 0, sizeof S);
+    const int n = (int)ctx->objs.size();
+    ctx->fp32_ok = true;
+    ctx->fp32_why.clear();
+    if (n > PT_MAX_OBJ) { ctx->fp32_ok = false; ctx->fp32_why = "more than 512 objects"; return; }
+    S.n_obj = n;
+    int nr = 0;
+    for (int axis = 0; axis < 3; axis++) {       // XZ, XY, YZ
+        S.rect_begin[axis] = nr;
+        const int want = axis == 0 ? OT_XZ : axis == 1 ? OT_XY : OT_YZ;
+        for (int i = 0; i < n; i++) {
+            const DevObj64 &o = ctx->objs[i];
+            if (o.type != want) continue;
+            S.rect_a[nr] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
+            S.rect_b[nr] = make_float2((float)o.g[3], 0.f);
+            std::memcpy(&S.rect_b[nr].y, &i, sizeof(int));
+            nr++;
+        }
+    }
+    S.rect_begin[3] = nr;
+    for (int i = 0; i < n; i++) {
+        const DevObj64 &o = ctx->objs[i];
+        if (o.type == OT_SPHERE) {
+            if (o.g[0] >= PT_HUGE_RADIUS) {
+                if (S.n_huge >= PT_MAX_HUGE) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 huge spheres"; return; }
+                double *h = S.huge[S.n_huge];
+                h[0] = o.g[1]; h[1] = o.g[2]; h[2] = o.g[3]; h[3] = o.g[0] * o.g[0];
+                S.huge_id[S.n_huge++] = i;
+            } else {
+                S.sph[S.n_sph] = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(o.g[0] * o.g[0]));
+                S.sph_id[S.n_sph++] = i;
+            }
+            if ((o.e[0] > 0 || o.e[1] > 0 || o.e[2] > 0) && S.n_lights < 32) S.light_sph[S.n_lights++] = i;
+        } else if (o.type == OT_TILT) {
+            if (S.n_tilt >= PT_MAX_TILT) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 tilted planes"; return; }
+            float4 *t = S.tilt[S.n_tilt++];
+            auto dotp = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+            t[0] = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], (float)dotp(o.n, o.p0));
+            t[1] = make_float4((float)o.s[0], (float)o.s[1], (float)o.s[2], (float)dotp(o.s, o.p0));
+            t[2] = make_float4((float)o.t[0], (float)o.t[1], (float)o.t[2], (float)dotp(o.t, o.p0));
+            t[3] = make_float4((float)o.hs, (float)o.ht, 0.f, 0.f);
+            std::memcpy(&t[3].z, &i, sizeof(int));
+        }
+    }
+    S.light_id = ctx->light.id;
+    S.lx0 = (float)ctx->light.x0; S.lxw = (float)ctx->light.xw;
+    S.lz0 = (float)ctx->light.z0; S.lzw = (float)ctx->light.zw;
+    S.ly = (float)ctx->light.y; S.larea = (float)ctx->light.area;
+}
+
+extern "C" {
+
+const char *pt_version(void) { return "ptb200 0.1 (sm_100a)"; }
+
+const char *pt_last_error(pt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
+{
+    if (!out || !scene) return pt_fail(nullptr, PT_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int n = scene->n_spheres + scene->n_planes;
+    if (n <= 0 || n > PT_MAX_OBJECTS) return pt_fail(nullptr, PT_ERR_ARG, "object count must be in 1..1024");
+    if (scene->n_spheres < 0 || scene->n_planes < 0) return pt_fail(nullptr, PT_ERR_ARG, "negative object count");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return pt_fail(nullptr, PT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)");
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) return pt_fail(nullptr, PT_ERR_ARG, "device index out of range");
+
+    pt_ctx *ctx = new (std::nothrow) pt_ctx();
+    if (!ctx) return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed");
+    ctx->device = device;
+    // flatten the table in id order (the reference's rect[] order, src/smallpt.cpp:287-311)
+    ctx->objs.resize(n);
+    for (int i = 0; i < n; i++) {
+        const int ref = scene->order ? scene->order[i] : (i < scene->n_planes ? i : ~(i - scene->n_planes));
+        DevObj64 o;
+        std::memset(&o, 0, sizeof o);
+        if (ref < 0) {
+            const int j = ~ref;
+            if (j >= scene->n_spheres) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "order[] names a sphere that does not exist"); }
+            const pt_sphere &s = scene->spheres[j];
+            if (!(s.rad > 0) || !finite3(s.p)) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad sphere"); }
+            o.type = OT_SPHERE; o.refl = s.refl;
+            o.g[0] = s.rad; o.g[1] = s.p.x; o.g[2] = s.p.y; o.g[3] = s.p.z;
+            o.e[0] = s.e.x; o.e[1] = s.e.y; o.e[2] = s.e.z; o.c[0] = s.c.x; o.c[1] = s.c.y; o.c[2] = s.c.z;
+        } else {
+            if (ref >= scene->n_planes) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "order[] names a plane that does not exist"); }
+            const pt_plane &p = scene->planes[ref];
+            if (p.kind < PT_PLANE_XZ || p.kind > PT_PLANE_TILTED) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad plane kind"); }
+            o.type = p.kind == PT_PLANE_XZ ? OT_XZ : p.kind == PT_PLANE_XY ? OT_XY : p.kind == PT_PLANE_YZ ? OT_YZ : OT_TILT;
+            o.refl = p.refl;
+            o.g[0] = p.a1; o.g[1] = p.a2; o.g[2] = p.b1; o.g[3] = p.b2; o.g[4] = p.k;
+            o.p0[0] = p.p0.x; o.p0[1] = p.p0.y; o.p0[2] = p.p0.z; o.n[0] = p.n.x; o.n[1] = p.n.y; o.n[2] = p.n.z;
+            o.s[0] = p.s.x; o.s[1] = p.s.y; o.s[2] = p.s.z; o.t[0] = p.t.x; o.t[1] = p.t.y; o.t[2] = p.t.z;
+            o.hs = p.hs; o.ht = p.ht;
+            o.e[0] = p.e.x; o.e[1] = p.e.y; o.e[2] = p.e.z; o.c[0] = p.c.x; o.c[1] = p.c.y; o.c[2] = p.c.z;
+        }
+        if (o.refl < PT_DIFF || o.refl > PT_REFR) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad material"); }
+        ctx->objs[i] = o;
+    }
+    ctx->cam = scene->camera;
+    ctx->light = scene->light;
+
+#define UP_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            int rc_ = pt_fail(nullptr, PT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            pt_destroy(ctx);                                                                            \
+            return rc_;                                                                                 \
+        }                                                                                               \
+    } while (0)
+
+    UP_CUDA(cudaSetDevice(device));
+    UP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    UP_CUDA(cudaEventCreate(&ctx->ev0));
+    UP_CUDA(cudaEventCreate(&ctx->ev1));
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->l2_bytes, cudaDevAttrL2CacheSize, device);
+    UP_CUDA(cudaMalloc(&ctx->d_objs, sizeof(DevObj64) * n));
+    UP_CUDA(cudaMemcpy(ctx->d_objs, ctx->objs.data(), sizeof(DevObj64) * n, cudaMemcpyHostToDevice));
+    UP_CUDA(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+    ctx->h_scene32 = new (std::nothrow) SceneF32;
+    if (!ctx->h_scene32) { pt_destroy(ctx); return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed"); }
+    build_scene_f32(ctx);
+    {
+        std::vector<MatF32> mats(n);
+        for (int i = 0; i < n; i++) {
+            const DevObj64 &o = ctx->objs[i];
+            MatF32 m;
+            m.c_refl = make_float4((float)o.c[0], (float)o.c[1], (float)o.c[2], 0.f);
+            std::memcpy(&m.c_refl.w, &o.refl, sizeof(int));
+            m.e_type = make_float4((float)o.e[0], (float)o.e[1], (float)o.e[2], 0.f);
+            std::memcpy(&m.e_type.w, &o.type, sizeof(int));
+            if (o.type == OT_SPHERE) m.geom = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(1.0 / o.g[0]));
+            else if (o.type == OT_TILT) m.geom = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], 0.f);
+            else m.geom = make_float4((float)o.g[4], 0.f, 0.f, 0.f);
+            mats[i] = m;
+        }
+        UP_CUDA(cudaMalloc(&ctx->d_mats, sizeof(MatF32) * n));
+        UP_CUDA(cudaMemcpy(ctx->d_mats, mats.data(), sizeof(MatF32) * n, cudaMemcpyHostToDevice));
+    }
+#undef UP_CUDA
+    *out = ctx;
+    return PT_OK;
+}
+
+static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum, cudaStream_t ext_stream)
+{
+    if (!ctx || !p) return pt_fail(ctx, PT_ERR_ARG, "null argument");
+    if (p->width <= 0 || p->height <= 0 || p->spp < 0 || p->width > 65535 || p->height > 65535)
+        return pt_fail(ctx, PT_ERR_ARG, "width/height must be in 1..65535 and spp >= 0");
+    if (p->mode < PT_MODE_NEE_REF_RECT || p->mode > PT_MODE_NEE_CONE_SPHERE) return pt_fail(ctx, PT_ERR_ARG, "bad mode");
+    if (p->engine != PT_ENGINE_FP32_PHILOX && p->engine != PT_ENGINE_FP64_ERAND48) return pt_fail(ctx, PT_ERR_ARG, "bad engine");
+    const int world = p->world > 0 ? p->world : 1;
+    if (p->rank < 0 || p->rank >= world) return pt_fail(ctx, PT_ERR_ARG, "rank must be in [0, world)");
+    if (p->mode == PT_MODE_NEE_REF_RECT && (ctx->light.id < 0 || ctx->light.id >= (int)ctx->objs.size()))
+        return pt_fail(ctx, PT_ERR_ARG, "PT_MODE_NEE_REF_RECT needs pt_scene.light.id to name a scene object");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ext_stream ? ext_stream : ctx->stream;
+    const size_t n_acc = (size_t)p->width * p->height * 3;
+    if (ctx->accum_elems < n_acc) {
+        if (ctx->d_sum) cudaFree(ctx->d_sum);
+        if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
+        ctx->d_sum = ctx->d_sumsq = nullptr; ctx->accum_elems = 0;
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_sum, n_acc * sizeof(double)));
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_sumsq, n_acc * sizeof(double)));
+        ctx->accum_elems = n_acc;
+    }
+    double *d_sum = ext_sum ? ext_sum : ctx->d_sum;
+    ctx->d_sum_ext = ext_sum;
+    PT_CUDA(ctx, cudaMemsetAsync(d_sum, 0, n_acc * sizeof(double), s));
+    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_sumsq, 0, n_acc * sizeof(double), s));
+    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), s));
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->last = *p;
+    ctx->rendered = false;
+    PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, ctx->d_sumsq, s)
+                                                 : pt_fp32_render(ctx, p, d_sum, ctx->d_sumsq, s);
+    if (rc) return rc;
+    PT_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    PT_CUDA(ctx, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    PT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    DevStats ds;
+    PT_CUDA(ctx, cudaMemcpy(&ds, ctx->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+    pt_stats &st = ctx->stats;
+    st.render_ms = ms;
+    st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
+    st.shaded_vertices = ds.shaded; st.max_depth_seen = ds.max_depth_seen;
+    if (p->engine == PT_ENGINE_FP64_ERAND48) {
+        st.paths = ds.paths; st.rays_camera = ds.rays_camera; st.rays_scatter = ds.rays_scatter;
+    } else {
+        // every generated path is one camera ray; scatter rays are the continuing paths counted on the device
+        long long owned_rows = 0;
+        const int tile = p->tile_rows > 0 ? p->tile_rows : 8, n_tiles = (p->height + tile - 1) / tile;
+        for (int k = p->rank; k < n_tiles; k += world) owned_rows += (k * tile + tile <= p->height) ? tile : (p->height - k * tile);
+        st.paths = (uint64_t)owned_rows * p->width * p->spp;
+        st.rays_camera = st.paths;
+        st.rays_scatter = ds.rays_scatter;
+    }
+    ctx->rendered = true;
+    return PT_OK;
+}
+
+int pt_render(pt_ctx *ctx, const pt_render_params *p) { return render_common(ctx, p, nullptr, nullptr); }
+
+int pt_render_into(pt_ctx *ctx, const pt_render_params *p, void *dev_rgb_sum, void *stream)
+{
+    if (!dev_rgb_sum) return pt_fail(ctx, PT_ERR_ARG, "null device buffer");
+    return render_common(ctx, p, (double *)dev_rgb_sum, (cudaStream_t)stream);
+}
+
+int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats)
+{
+    if (!ctx) return pt_fail(ctx, PT_ERR_ARG, "null context");
+    if (!ctx->rendered) return pt_fail(ctx, PT_ERR_STATE, "pt_readback before a successful pt_render");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const pt_render_params &p = ctx->last;
+    const size_t n = (size_t)p.width * p.height * 3;
+    if (rgb_mean) {
+        const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
+        PT_CUDA(ctx, cudaMemcpy(rgb_mean, src, n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (p.spp > 0) for (size_t i = 0; i < n; i++) rgb_mean[i] = rgb_mean[i] / p.spp;
+    }
+    if (rgb_sumsq) {
+        if (!p.collect_stats) return pt_fail(ctx, PT_ERR_STATE, "sum of squares requested but collect_stats was 0");
+        PT_CUDA(ctx, cudaMemcpy(rgb_sumsq, ctx->d_sumsq, n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (stats) *stats = ctx->stats;
+    return PT_OK;
+}
+
+void *pt_accum_device_ptr(pt_ctx *ctx) { return ctx ? (void *)(ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum) : nullptr; }
+
+int pt_debug_intersect(pt_ctx *ctx, const double *rays_od, int n, int precision, double *t_out, int *id_out)
+{
+    if (!ctx || !rays_od || !t_out || !id_out || n < 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    if (precision != 32 && precision != 64) return pt_fail(ctx, PT_ERR_ARG, "precision must be 32 or 64");
+    if (n == 0) return PT_OK;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d_r = nullptr, *d_t = nullptr;
+    int *d_id = nullptr;
+    PT_CUDA(ctx, cudaMalloc(&d_r, sizeof(double) * 6 * (size_t)n));
+    PT_CUDA(ctx, cudaMalloc(&d_t, sizeof(double) * (size_t)n));
+    PT_CUDA(ctx, cudaMalloc(&d_id, sizeof(int) * (size_t)n));
+    int rc = PT_OK;
+    cudaError_t e = cudaMemcpyAsync(d_r, rays_od, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        rc = precision == 64 ? pt_fp64_intersect(ctx, d_r, n, d_t, d_id, ctx->stream) : pt_fp32_intersect(ctx, d_r, n, d_t, d_id, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(id_out, d_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_r); cudaFree(d_t); cudaFree(d_id);
+    if (rc != PT_OK) return rc;
+    if (e != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_debug_intersect: ") + cudaGetErrorString(e));
+    return PT_OK;
+}
+
+int pt_debug_erand48(pt_ctx *ctx, const uint16_t *seeds, int n_threads, int draws, double *out)
+{
+    if (!ctx || !seeds || !out || n_threads <= 0 || draws <= 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint16_t *d_s = nullptr;
+    double *d_o = nullptr;
+    PT_CUDA(ctx, cudaMalloc(&d_s, sizeof(uint16_t) * 3 * (size_t)n_threads));
+    PT_CUDA(ctx, cudaMalloc(&d_o, sizeof(double) * (size_t)n_threads * draws));
+    cudaError_t e = cudaMemcpyAsync(d_s, seeds, sizeof(uint16_t) * 3 * (size_t)n_threads, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = PT_OK;
+    if (e == cudaSuccess) rc = pt_fp64_erand48(ctx, d_s, n_threads, draws, d_o, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)n_threads * draws, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_s); cudaFree(d_o);
+    if (rc != PT_OK) return rc;
+    if (e != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_debug_erand48: ") + cudaGetErrorString(e));
+    return PT_OK;
+}
+
+int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out)
+{
+    if (!ctx || !ctr || !key || !out || n <= 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t *d_c = nullptr, *d_k = nullptr, *d_o = nullptr;
+    PT_CUDA(ctx, cudaMalloc(&d_c, sizeof(uint32_t) * 4 * (size_t)n));
+    PT_CUDA(ctx, cudaMalloc(&d_k, sizeof(uint32_t) * 2 * (size_t)n));
+    PT_CUDA(ctx, cudaMalloc(&d_o, sizeof(uint32_t) * 4 * (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(d_c, ctr, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, key, sizeof(uint32_t) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = PT_OK;
+    if (e == cudaSuccess) rc = pt_fp32_philox(ctx, d_c, d_k, n, d_o, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_c); cudaFree(d_k); cudaFree(d_o);
+    if (rc != PT_OK) return rc;
+    if (e != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_debug_philox: ") + cudaGetErrorString(e));
+    return PT_OK;
+}
+
+int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz)
+{
+    if (!ctx || !tflops || !sm_clock_mhz) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return pt_fp32_ffma_peak(ctx, tflops, sm_clock_mhz);
+}
+
+void pt_destroy(pt_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 4; b++) if (ctx->q[a][b]) cudaFree(ctx->q[a][b]);
+    if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->d_fix) cudaFree(ctx->d_fix);
+    if (ctx->d_fixsq) cudaFree(ctx->d_fixsq);
+    if (ctx->d_sum) cudaFree(ctx->d_sum);
+    if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
+    if (ctx->d_objs) cudaFree(ctx->d_objs);
+    if (ctx->d_mats) cudaFree(ctx->d_mats);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->h_scene32;
+    delete ctx;
+}
+
+}  // extern "C"
