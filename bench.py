@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark: Mpaths/s of the per-pixel Monte Carlo radiance loop (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (B200, CUDA kernels through the C ABI)
+  python bench.py --impl reference [...]                    the reference's own CPU code on the host cores
+
+One "step" = one full render of the workload.
+  N = 1 : BASELINE.json configs[1] — built-in scene (HEAD, 17 rectangles), 512x512, 512 spp, explicit light
+          sampling (the reference's NEE) + Russian roulette, production FP32 Philox engine.
+  N > 1 : BASELINE.json configs[4] — same scene and integrator at 3840x2160, 1024 spp, interleaved 16-row tiles
+          sharded over the ranks, accumulation buffers gathered to rank 0 over NCCL (total work fixed: strong).
+`value` = paths of the whole job / device time (max over ranks), inputs resident on the device.
+`e2e`   = the same metric through the C ABI with HOST buffers: scene upload (H2D), render, gather, read-back
+          of the FP64 image to host memory (D2H), wall clock, every step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpaths/s"
+WORKLOADS = {
+    # name: (scene, width, height, spp, mode, description)
+    "c2": ("A", 512, 512, 512, 0, "C2: built-in scene A 512x512, 512 spp, NEE_REF_RECT + Russian roulette"),
+    "c1": ("A", 512, 512, 16, 1, "C1: built-in scene A 512x512, 16 spp, cosine-weighted"),
+    "c3": ("A", 512, 512, 32, 2, "C3: built-in scene A 512x512, 32 spp, uniform hemisphere"),
+    "c4": ("synthetic", 1920, 1080, 256, 1, "C4: synthetic 256 spheres + tilted planes 1920x1080, 256 spp, cosine"),
+    "c5": ("A", 3840, 2160, 1024, 0, "C5: built-in scene A 3840x2160, 1024 spp, NEE_REF_RECT, row-tile sharded + NCCL gather"),
+}
+F_SHADE = {0: 150.0, 1: 110.0, 2: 110.0, 3: 150.0}     # algorithmic FLOPs per shaded bounce, SURVEY 8(d)
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # clocks under load: the upper half of the samples (the sampler also sees idle gaps between steps)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(workload, budget_s, threads=0):
+    """Time the reference's own CPU implementation (oracle/_ref/smallpt_ref: src/smallpt.cpp + patches P0-P6) on
+    a bounded sample of the workload: same scene/mode/resolution, reduced spp.  Falls back to the C port."""
+    scene, w, h, spp, mode, _ = WORKLOADS[workload]
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "smallpt_ref")
+    scene_arg = {"A": "A", "B": "B", "C": "C"}.get(scene)
+    ncores = os.cpu_count() or 1
+    threads = threads or ncores
+
+    def run_ref(s):
+        out = subprocess.check_output([ref_bin, str(s), str(mode), scene_arg, str(w), str(h), "", "0", str(threads)], text=True)
+        return json.loads(out.strip().splitlines()[-1])
+
+    def run_port(s):
+        from _pkg import ptb
+        L = ptb.load_oracle()
+        L.oracle_set_threads(threads)
+        sc = ptb.builtin_scene(scene, w, h)
+        st = ptb.oracle_render(sc, ptb.params(w, h, s, mode=mode, engine=1))[3]
+        return {"paths": float(st.paths), "render_ms": st.render_ms, "threads": st.threads}
+
+    kind = "reference" if (os.path.exists(ref_bin) and scene_arg) else "port"
+    run = run_ref if kind == "reference" else run_port
+    res = run(2)                                                     # probe, then grow the sample to the budget
+    s = 2
+    for _ in range(3):
+        rate = res["paths"] / max(res["render_ms"], 1e-3)            # paths per ms
+        s_next = int(max(1, min(spp, budget_s * 1e3 * rate / (w * h))))
+        if res["render_ms"] >= 0.5 * budget_s * 1e3 or s_next <= s:
+            break
+        s = s_next
+        res = run(s)
+    return {"value": res["paths"] / res["render_ms"] * 1e-3, "unit": METRIC, "cores": int(res["threads"]), "kind": kind,
+            "sample": f"{WORKLOADS[workload][5].split(':')[0]} scene/mode/resolution at {s} spp ({res['paths']:.0f} paths, "
+                      f"{res['render_ms'] / 1e3:.1f} s), OpenMP schedule(dynamic,1) over rows, host has {ncores} cores"}, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    workload = args.workload or ("c2" if n_gpus == 1 else "c5")
+    scene_name, w, h, spp, mode, desc = WORKLOADS[workload]
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        info = None
+        per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        for i in range(args.warmup + args.steps):
+            info, res = cpu_reference(workload, per_step)
+            if i >= args.warmup:
+                vals.append((res["paths"], res["render_ms"]))
+        paths = sum(v[0] for v in vals)
+        ms = sum(v[1] for v in vals)
+        value = paths / ms * 1e-3
+        info["value"] = value
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / max(1, args.steps), "higher_is_better": True,
+                "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "note": "CPU: each step is a bounded sample (reduced spp) of the workload"},
+                "cpu_baseline": info,
+                "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    import numpy as np
+    import torch
+    from _pkg import ptb
+    from small_pathtracer_b200 import dist as pdist
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    tile_rows = 16 if world > 1 else 8
+    scene = ptb.builtin_scene(scene_name, w, h)
+    ctx = ptb.Context(scene, device=local_rank)
+    params = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=rank, world=world)
+    stream = torch.cuda.Stream(device)        # the kernels, the gather and the timing events all live on this stream
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step(timed):
+        """one render of this rank's tiles + gather to rank 0; returns (device ms, stats)"""
+        flush.fill_(1)                                                    # L2 flush between iterations
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        local = torch.empty((h, w, 3), dtype=torch.float64, device=device)
+        e0.record(stream)
+        ctx.render_into(params, local.data_ptr(), stream.cuda_stream)
+        st = ctx.stats()
+        full = pdist.gather_rows(local, h, tile_rows, rank, world, dst=0) if world > 1 else local
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)              # render (all k_bounce launches + resolve) + gather, on `stream`
+        return ms, st, full
+
+    for _ in range(warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    ms_steps, stats, launches, kernel_ms, iters = [], None, 0, 0.0, 0
+    for _ in range(args.steps):
+        ms, st, full = step(True)
+        ms_steps.append(ms)
+        stats = st
+        launches += st.kernel_launches
+        kernel_ms += st.render_ms
+        iters += st.iterations
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop()
+    total_ms = sum(ms_steps)
+    my_paths = float(stats.paths) * args.steps
+    my_rays = float(stats.rays) * args.steps
+    my_shaded = float(stats.shaded_vertices) * args.steps
+    agg = torch.tensor([total_ms, my_paths, my_rays, my_shaded, float(launches), kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        tmax = agg[:1].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sums = agg[1:].clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        total_ms = float(tmax[0])
+        paths, rays, shaded, launches_all, kernel_ms_all = (float(x) for x in sums)
+    else:
+        paths, rays, shaded, launches_all, kernel_ms_all = my_paths, my_rays, my_shaded, float(launches), kernel_ms
+    value = paths / total_ms * 1e-3
+    mrays = rays / total_ms * 1e-3
+
+    # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    def e2e_step():
+        t0 = time.perf_counter()
+        c2 = ptb.Context(scene, device=local_rank)                         # H2D: scene table + camera
+        if world > 1:
+            full, local = pdist.render_sharded(c2, params, device, dst=0)
+            host = full.cpu().numpy() if rank == 0 else None                # D2H: assembled image
+        else:
+            c2.render(params)
+            host, _ = c2.readback()                                         # D2H inside pt_readback
+        c2.close()
+        if world > 1:
+            dist.barrier()
+        return time.perf_counter() - t0, host
+    e2e_step()
+    barrier()
+    e2e_times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        dt, host_img = e2e_step()
+        e2e_times.append(dt)
+    e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = (paths / args.steps) * len(e2e_times) / float(e2e_t[0]) * 1e-6
+    import ctypes as C
+    h2d = scene.n_spheres * C.sizeof(ptb.Sphere) + scene.n_planes * C.sizeof(ptb.Plane) + 4 * scene.n_objects + C.sizeof(ptb.Camera) + C.sizeof(ptb.Light)
+    d2h = w * h * 3 * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ roofline (rank 0's dominant kernel: k_bounce)
+    peaks, peak_src = read_peaks()
+    try:
+        ffma_tf, _ = ctx.ffma_peak()
+    except Exception:
+        ffma_tf = None
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    fp32_theory = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    f_isect = scene.flops_per_ray()
+    my_flops = float(stats.rays) * f_isect + float(stats.shaded_vertices) * F_SHADE[mode]     # per step, this rank
+    k_ms = stats.render_ms                                                                   # CUDA events around the launches
+    achieved_tf = my_flops / (k_ms * 1e-3) / 1e12
+    per_launch_ms = k_ms / max(1, stats.iterations)
+    qbytes = 96.0 * (float(stats.shaded_vertices))                     # 48 B read + 48 B written per path-iteration (upper bound)
+    roofline = {"bound": "fp32", "kernel": "k_bounce", "achieved": achieved_tf, "peak": ffma_tf or fp32_theory, "unit": "TFLOP/s",
+                "frac": achieved_tf / (ffma_tf or fp32_theory),
+                "peak_source": "FFMA-only microbenchmark measured in this run (pt_debug_ffma_peak)" if ffma_tf else "148 SM x 128 lanes x 2 x sm_max_mhz",
+                "peak_theoretical": fp32_theory, "frac_of_theoretical": achieved_tf / fp32_theory,
+                "flops_per_ray": f_isect, "flops_per_bounce": F_SHADE[mode],
+                "avg_launch_ms": per_launch_ms, "launches_per_step": int(stats.iterations),
+                "traffic": None,
+                "queue": {"bound": "hbm", "achieved": qbytes / (k_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                          "frac": qbytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
+                          "note": "algorithmic queue bytes (96 B per path-iteration); the queues are L2-resident by design"}}
+    line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "engine": "FP32 Philox wavefront", "tile_rows": tile_rows, "parallelism": f"row-tiles x{world}",
+                       "l2": "256 MiB flush write between timed iterations", "paths_per_step": paths / args.steps,
+                       "rays_per_path": rays / paths, "seed": 0},
+            "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
+            "clocks": clocks, "gpu_launches": int(launches_all),
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "pt_scene_upload + pt_render + pt_readback (FP64 image to host) per step, wall clock"},
+            "roofline": roofline}
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        try:
+            info, _ = cpu_reference(workload, args.cpu_budget)
+            line["cpu_baseline"] = info
+        except Exception as e:                                           # the CPU leg must never sink the GPU number
+            line["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -478,3 +478,22 @@ int oracle_write_ppm(const char *path, const double *rgb, int w, int h)
 }
 
 void oracle_det_sincos(double a, double *s, double *c) { pt_det_sincos(a, s, c); }
+
+/* random_scattering(nl, Xi), :337-360, exported for the golden-vector test. */
+void oracle_random_scattering(const double *nl, unsigned short *xi, int mode, int sincos, double *d_out)
+{
+    Ctx cx = { 0, mode, sincos, 0, xi, 0 };
+    V d = random_scattering(&cx, v3(nl[0], nl[1], nl[2]));
+    d_out[0] = d.x; d_out[1] = d.y; d_out[2] = d.z;
+}
+
+/* number of OpenMP threads used by oracle_render / oracle_intersect (0 = leave as is); returns the maximum */
+int oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}

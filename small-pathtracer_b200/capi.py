@@ -307,6 +307,11 @@ class Context:
             return mean, sq.reshape(p.height, p.width, 3), st
         return mean, st
 
+    def stats(self):
+        st = Stats()
+        self._check(lib().pt_readback(self._h, None, None, C.byref(st)), "pt_readback")
+        return st
+
     def accum_ptr(self):
         return lib().pt_accum_device_ptr(self._h)
 

@@ -1,0 +1,60 @@
+"""Row-tile sharding across GPUs + gather to rank 0.
+
+One process per GPU (torchrun); torch.distributed is the plumbing.  Tile k (tile_rows rows) belongs to
+rank k % world — interleaved so that ceiling/light rows (short paths) and floor rows (deep paths) spread
+evenly.  Each rank renders its tiles with pt_render_into() straight into a torch tensor, packs its owned
+rows and one gather (NCCL send/recv over NVLink; gloo in the CPU tests) brings them to rank 0, which
+de-interleaves.  No reduction is involved: every pixel lives on exactly one rank, so the N-GPU image is
+bit-identical to the 1-GPU image.
+"""
+import numpy as np
+
+
+def owned_rows(height, tile_rows, rank, world):
+    """Row indices owned by `rank` (ascending)."""
+    tile_rows = tile_rows if tile_rows > 0 else 8
+    rows = np.arange(height)
+    return rows[(rows // tile_rows) % world == rank]
+
+
+def gather_rows(local_full, height, tile_rows, rank, world, dst=0, group=None):
+    """local_full: (H, W, 3) tensor holding this rank's owned rows (other rows ignored).
+    Returns the assembled (H, W, 3) tensor on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    tile_rows = tile_rows if tile_rows > 0 else 8
+    counts = [len(owned_rows(height, tile_rows, r, world)) for r in range(world)]
+    max_rows = max(counts)
+    mine = torch.as_tensor(owned_rows(height, tile_rows, rank, world), device=local_full.device, dtype=torch.long)
+    packed = local_full.new_zeros((max_rows,) + tuple(local_full.shape[1:]))
+    if len(mine):
+        packed[:len(mine)] = local_full.index_select(0, mine)
+    if world == 1:
+        parts = [packed]
+    else:
+        parts = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+        dist.gather(packed, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.zeros_like(local_full)
+    for r in range(world):
+        idx = torch.as_tensor(owned_rows(height, tile_rows, r, world), device=local_full.device, dtype=torch.long)
+        if len(idx):
+            out.index_copy_(0, idx, parts[r][:len(idx)])
+    return out
+
+
+def render_sharded(ctx, params, device, dst=0, group=None):
+    """Render this rank's row tiles on `device` into a torch tensor (per-pixel SUM of sample radiance,
+    FP64) and gather to rank `dst`.  Returns (image_sum on dst | None, local tensor)."""
+    import torch
+    # torch.empty: the library zeroes the buffer itself on the render stream (no torch kernel to race with)
+    local = torch.empty((params.height, params.width, 3), dtype=torch.float64, device=device)
+    stream = torch.cuda.current_stream(device)
+    stream.synchronize()
+    # stream handle 0 (torch's legacy default stream) makes the library use its own non-blocking stream;
+    # pt_render_into is synchronous on return either way
+    ctx.render_into(params, local.data_ptr(), stream.cuda_stream)
+    world = params.world if params.world > 0 else 1
+    full = gather_rows(local, params.height, params.tile_rows, params.rank, world, dst=dst, group=group)
+    return full, local
