@@ -47,55 +47,69 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every ~5 ms
+    (nvidia-smi -lms cannot resolve a region that lasts tens of milliseconds)."""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.samples = []          # (t, sm_mhz, reasons bitmask)
+        self.ok = False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML device through its UUID/PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # noqa: BLE001
+            self.err = str(e)
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        if not self.ok:
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        # clocks under load: the upper half of the samples (the sampler also sees idle gaps between steps)
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:       # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:           # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def stop(self, t0=None, t1=None):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "")}
+        self._stop.set()
+        self.thread.join(timeout=1)
+        rows = [r for r in self.samples if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in rows))
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_reference(workload, budget_s, threads=0):
@@ -222,8 +236,9 @@ def main():
     for _ in range(warmup):
         step(False)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    time.sleep(0.05)
+    barrier()
     t_wall0 = time.perf_counter()
     ms_steps, stats, launches, kernel_ms, iters = [], None, 0, 0.0, 0
     for _ in range(args.steps):
@@ -235,7 +250,7 @@ def main():
         iters += st.iterations
     barrier()
     t_wall1 = time.perf_counter()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall1)
     total_ms = sum(ms_steps)
     my_paths = float(stats.paths) * args.steps
     my_rays = float(stats.rays) * args.steps

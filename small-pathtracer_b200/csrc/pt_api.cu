@@ -146,6 +146,10 @@ int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
     UP_CUDA(cudaMalloc(&ctx->d_objs, sizeof(DevObj64) * n));
     UP_CUDA(cudaMemcpy(ctx->d_objs, ctx->objs.data(), sizeof(DevObj64) * n, cudaMemcpyHostToDevice));
     UP_CUDA(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
+    UP_CUDA(cudaMallocHost(&ctx->h_pinned, 2 * sizeof(unsigned int)));
+    UP_CUDA(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
+    UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[0], cudaEventDisableTiming));
+    UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[1], cudaEventDisableTiming));
     ctx->h_scene32 = new (std::nothrow) SceneF32;
     if (!ctx->h_scene32) { pt_destroy(ctx); return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed"); }
     build_scene_f32(ctx);
@@ -196,21 +200,21 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     double *d_sum = ext_sum ? ext_sum : ctx->d_sum;
     ctx->d_sum_ext = ext_sum;
     PT_CUDA(ctx, cudaMemsetAsync(d_sum, 0, n_acc * sizeof(double), s));
-    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_sumsq, 0, n_acc * sizeof(double), s));
+    if (p->collect_stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_sumsq, 0, n_acc * sizeof(double), s));
     PT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), s));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->last = *p;
     ctx->rendered = false;
     PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, ctx->d_sumsq, s)
+    int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, p->collect_stats ? ctx->d_sumsq : nullptr, s)
                                                  : pt_fp32_render(ctx, p, d_sum, ctx->d_sumsq, s);
     if (rc) return rc;
     PT_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
     PT_CUDA(ctx, cudaStreamSynchronize(s));
     float ms = 0.f;
     PT_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    DevStats ds;
-    PT_CUDA(ctx, cudaMemcpy(&ds, ctx->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+    const DevStats ds = *ctx->h_stats;
     pt_stats &st = ctx->stats;
     st.render_ms = ms;
     st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
@@ -345,6 +349,10 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_objs) cudaFree(ctx->d_objs);
     if (ctx->d_mats) cudaFree(ctx->d_mats);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->ev_batch[0]) cudaEventDestroy(ctx->ev_batch[0]);
+    if (ctx->ev_batch[1]) cudaEventDestroy(ctx->ev_batch[1]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

