@@ -271,14 +271,13 @@ def main():
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
     def e2e_step():
         t0 = time.perf_counter()
-        c2 = ptb.Context(scene, device=local_rank)                         # H2D: scene table + camera
+        ctx.update_scene(scene)                                             # H2D: scene table + camera (pt_scene_upload, in place)
         if world > 1:
-            full, local = pdist.render_sharded(c2, params, device, dst=0)
+            full, local = pdist.render_sharded(ctx, params, device, dst=0)
             host = full.cpu().numpy() if rank == 0 else None                # D2H: assembled image
         else:
-            c2.render(params)
-            host, _ = c2.readback()                                         # D2H inside pt_readback
-        c2.close()
+            ctx.render(params)
+            host, _ = ctx.readback()                                        # D2H inside pt_readback
         if world > 1:
             dist.barrier()
         return time.perf_counter() - t0, host
@@ -334,7 +333,7 @@ def main():
             "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
             "clocks": clocks, "gpu_launches": int(launches_all),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pt_scene_upload + pt_render + pt_readback (FP64 image to host) per step, wall clock"},
+                    "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback (FP64 image device->host) per step, wall clock"},
             "roofline": roofline}
     if n_gpus == 1 and not args.no_cpu_baseline:
         try:

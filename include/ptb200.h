@@ -161,7 +161,10 @@ typedef struct pt_ctx pt_ctx;
 
 /* Create a context on the current CUDA device (or `device` >= 0) and upload the scene
  * table + camera.  Replaces the global scene literal and Camera construction feeding the
- * loop, src/smallpt.cpp:287-311 and :521. */
+ * loop, src/smallpt.cpp:287-311 and :521.
+ * *ctx must be NULL to create a context.  If *ctx is an existing context, its scene is
+ * REPLACED in place (host -> device copy of the new tables) and its device buffers (queues,
+ * accumulators) are kept — the cheap path for rendering many scenes or frames. */
 int pt_scene_upload(pt_ctx **ctx, const pt_scene *scene, int device);
 
 /* Render: the whole triple loop rows x pixels x samples, src/smallpt.cpp:528-541, including

@@ -282,6 +282,12 @@ class Context:
             raise PtError(f"pt_scene_upload failed ({rc}): {msg.decode() if msg else ''}")
         self.last = None
 
+    def update_scene(self, scene):
+        """pt_scene_upload on the existing context: replace the scene, keep the device buffers."""
+        d = scene.desc()
+        self._check(lib().pt_scene_upload(C.byref(self._h), C.byref(d), -1), "pt_scene_upload(update)")
+        self.scene = scene
+
     def _check(self, rc, what):
         if rc:
             msg = lib().pt_last_error(self._h)

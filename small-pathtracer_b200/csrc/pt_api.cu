@@ -77,13 +77,93 @@ const char *pt_version(void) { return "ptb200 0.1 (sm_100a)"; }
 
 const char *pt_last_error(pt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
+// validation + flattening of the table in id order (the reference's rect[] order, src/smallpt.cpp:287-311); no CUDA
+static int flatten_scene(const pt_scene *scene, std::vector<DevObj64> &objs, std::string &why)
+{
+    const int n = scene->n_spheres + scene->n_planes;
+    objs.resize(n);
+    for (int i = 0; i < n; i++) {
+        const int ref = scene->order ? scene->order[i] : (i < scene->n_planes ? i : ~(i - scene->n_planes));
+        DevObj64 o;
+        std::memset(&o, 0, sizeof o);
+        if (ref < 0) {
+            const int j = ~ref;
+            if (j >= scene->n_spheres) { why = "order[] names a sphere that does not exist"; return PT_ERR_ARG; }
+            const pt_sphere &s = scene->spheres[j];
+            if (!(s.rad > 0) || !finite3(s.p)) { why = "bad sphere"; return PT_ERR_ARG; }
+            o.type = OT_SPHERE; o.refl = s.refl;
+            o.g[0] = s.rad; o.g[1] = s.p.x; o.g[2] = s.p.y; o.g[3] = s.p.z;
+            o.e[0] = s.e.x; o.e[1] = s.e.y; o.e[2] = s.e.z; o.c[0] = s.c.x; o.c[1] = s.c.y; o.c[2] = s.c.z;
+        } else {
+            if (ref >= scene->n_planes) { why = "order[] names a plane that does not exist"; return PT_ERR_ARG; }
+            const pt_plane &p = scene->planes[ref];
+            if (p.kind < PT_PLANE_XZ || p.kind > PT_PLANE_TILTED) { why = "bad plane kind"; return PT_ERR_ARG; }
+            o.type = p.kind == PT_PLANE_XZ ? OT_XZ : p.kind == PT_PLANE_XY ? OT_XY : p.kind == PT_PLANE_YZ ? OT_YZ : OT_TILT;
+            o.refl = p.refl;
+            o.g[0] = p.a1; o.g[1] = p.a2; o.g[2] = p.b1; o.g[3] = p.b2; o.g[4] = p.k;
+            o.p0[0] = p.p0.x; o.p0[1] = p.p0.y; o.p0[2] = p.p0.z; o.n[0] = p.n.x; o.n[1] = p.n.y; o.n[2] = p.n.z;
+            o.s[0] = p.s.x; o.s[1] = p.s.y; o.s[2] = p.s.z; o.t[0] = p.t.x; o.t[1] = p.t.y; o.t[2] = p.t.z;
+            o.hs = p.hs; o.ht = p.ht;
+            o.e[0] = p.e.x; o.e[1] = p.e.y; o.e[2] = p.e.z; o.c[0] = p.c.x; o.c[1] = p.c.y; o.c[2] = p.c.z;
+        }
+        if (o.refl < PT_DIFF || o.refl > PT_REFR) { why = "bad material"; return PT_ERR_ARG; }
+        objs[i] = o;
+    }
+    return PT_OK;
+}
+
+// host -> device copy of the scene tables (FP64 object table, FP32 material table) + the FP32 constant image
+static int upload_tables(pt_ctx *ctx)
+{
+    const int n = (int)ctx->objs.size();
+    if (ctx->n_alloc < n) {
+        if (ctx->d_objs) cudaFree(ctx->d_objs);
+        if (ctx->d_mats) cudaFree(ctx->d_mats);
+        ctx->d_objs = nullptr; ctx->d_mats = nullptr; ctx->n_alloc = 0;
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_objs, sizeof(DevObj64) * n));
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_mats, sizeof(MatF32) * n));
+        ctx->n_alloc = n;
+    }
+    build_scene_f32(ctx);
+    std::vector<MatF32> mats(n);
+    for (int i = 0; i < n; i++) {
+        const DevObj64 &o = ctx->objs[i];
+        MatF32 m;
+        m.c_refl = make_float4((float)o.c[0], (float)o.c[1], (float)o.c[2], 0.f);
+        std::memcpy(&m.c_refl.w, &o.refl, sizeof(int));
+        m.e_type = make_float4((float)o.e[0], (float)o.e[1], (float)o.e[2], 0.f);
+        std::memcpy(&m.e_type.w, &o.type, sizeof(int));
+        m.aux = make_float4((float)o.p0[0], (float)o.p0[1], (float)o.p0[2], 0.f);
+        if (o.type == OT_SPHERE) m.geom = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(1.0 / o.g[0]));
+        else if (o.type == OT_TILT) m.geom = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], 0.f);
+        else { const float khi = (float)o.g[4]; m.geom = make_float4(khi, (float)(o.g[4] - (double)khi), 0.f, 0.f); }
+        mats[i] = m;
+    }
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_objs, ctx->objs.data(), sizeof(DevObj64) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), sizeof(MatF32) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
 int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
 {
     if (!out || !scene) return pt_fail(nullptr, PT_ERR_ARG, "null argument");
-    *out = nullptr;
+    pt_ctx *reuse = *out;            // non-NULL: replace the scene of an existing context, keep its device buffers
     const int n = scene->n_spheres + scene->n_planes;
-    if (n <= 0 || n > PT_MAX_OBJECTS) return pt_fail(nullptr, PT_ERR_ARG, "object count must be in 1..1024");
-    if (scene->n_spheres < 0 || scene->n_planes < 0) return pt_fail(nullptr, PT_ERR_ARG, "negative object count");
+    if (scene->n_spheres < 0 || scene->n_planes < 0) return pt_fail(reuse, PT_ERR_ARG, "negative object count");
+    if (n <= 0 || n > PT_MAX_OBJECTS) return pt_fail(reuse, PT_ERR_ARG, "object count must be in 1..1024");
+    std::vector<DevObj64> objs;
+    std::string why;
+    if (flatten_scene(scene, objs, why) != PT_OK) return pt_fail(reuse, PT_ERR_ARG, why);
+    if (reuse) {
+        if (device >= 0 && device != reuse->device) return pt_fail(reuse, PT_ERR_ARG, "context lives on another device");
+        PT_CUDA(reuse, cudaSetDevice(reuse->device));
+        reuse->objs.swap(objs);
+        reuse->cam = scene->camera;
+        reuse->light = scene->light;
+        reuse->rendered = false;
+        return upload_tables(reuse);
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -95,35 +175,7 @@ int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
     pt_ctx *ctx = new (std::nothrow) pt_ctx();
     if (!ctx) return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed");
     ctx->device = device;
-    // flatten the table in id order (the reference's rect[] order, src/smallpt.cpp:287-311)
-    ctx->objs.resize(n);
-    for (int i = 0; i < n; i++) {
-        const int ref = scene->order ? scene->order[i] : (i < scene->n_planes ? i : ~(i - scene->n_planes));
-        DevObj64 o;
-        std::memset(&o, 0, sizeof o);
-        if (ref < 0) {
-            const int j = ~ref;
-            if (j >= scene->n_spheres) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "order[] names a sphere that does not exist"); }
-            const pt_sphere &s = scene->spheres[j];
-            if (!(s.rad > 0) || !finite3(s.p)) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad sphere"); }
-            o.type = OT_SPHERE; o.refl = s.refl;
-            o.g[0] = s.rad; o.g[1] = s.p.x; o.g[2] = s.p.y; o.g[3] = s.p.z;
-            o.e[0] = s.e.x; o.e[1] = s.e.y; o.e[2] = s.e.z; o.c[0] = s.c.x; o.c[1] = s.c.y; o.c[2] = s.c.z;
-        } else {
-            if (ref >= scene->n_planes) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "order[] names a plane that does not exist"); }
-            const pt_plane &p = scene->planes[ref];
-            if (p.kind < PT_PLANE_XZ || p.kind > PT_PLANE_TILTED) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad plane kind"); }
-            o.type = p.kind == PT_PLANE_XZ ? OT_XZ : p.kind == PT_PLANE_XY ? OT_XY : p.kind == PT_PLANE_YZ ? OT_YZ : OT_TILT;
-            o.refl = p.refl;
-            o.g[0] = p.a1; o.g[1] = p.a2; o.g[2] = p.b1; o.g[3] = p.b2; o.g[4] = p.k;
-            o.p0[0] = p.p0.x; o.p0[1] = p.p0.y; o.p0[2] = p.p0.z; o.n[0] = p.n.x; o.n[1] = p.n.y; o.n[2] = p.n.z;
-            o.s[0] = p.s.x; o.s[1] = p.s.y; o.s[2] = p.s.z; o.t[0] = p.t.x; o.t[1] = p.t.y; o.t[2] = p.t.z;
-            o.hs = p.hs; o.ht = p.ht;
-            o.e[0] = p.e.x; o.e[1] = p.e.y; o.e[2] = p.e.z; o.c[0] = p.c.x; o.c[1] = p.c.y; o.c[2] = p.c.z;
-        }
-        if (o.refl < PT_DIFF || o.refl > PT_REFR) { delete ctx; return pt_fail(nullptr, PT_ERR_ARG, "bad material"); }
-        ctx->objs[i] = o;
-    }
+    ctx->objs.swap(objs);
     ctx->cam = scene->camera;
     ctx->light = scene->light;
 
@@ -143,34 +195,16 @@ int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
     UP_CUDA(cudaEventCreate(&ctx->ev1));
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->l2_bytes, cudaDevAttrL2CacheSize, device);
-    UP_CUDA(cudaMalloc(&ctx->d_objs, sizeof(DevObj64) * n));
-    UP_CUDA(cudaMemcpy(ctx->d_objs, ctx->objs.data(), sizeof(DevObj64) * n, cudaMemcpyHostToDevice));
     UP_CUDA(cudaMalloc(&ctx->d_stats, sizeof(DevStats)));
     UP_CUDA(cudaMallocHost(&ctx->h_pinned, 2 * sizeof(unsigned int)));
     UP_CUDA(cudaMallocHost(&ctx->h_stats, sizeof(DevStats)));
     UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[0], cudaEventDisableTiming));
     UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[1], cudaEventDisableTiming));
+#undef UP_CUDA
     ctx->h_scene32 = new (std::nothrow) SceneF32;
     if (!ctx->h_scene32) { pt_destroy(ctx); return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed"); }
-    build_scene_f32(ctx);
-    {
-        std::vector<MatF32> mats(n);
-        for (int i = 0; i < n; i++) {
-            const DevObj64 &o = ctx->objs[i];
-            MatF32 m;
-            m.c_refl = make_float4((float)o.c[0], (float)o.c[1], (float)o.c[2], 0.f);
-            std::memcpy(&m.c_refl.w, &o.refl, sizeof(int));
-            m.e_type = make_float4((float)o.e[0], (float)o.e[1], (float)o.e[2], 0.f);
-            std::memcpy(&m.e_type.w, &o.type, sizeof(int));
-            if (o.type == OT_SPHERE) m.geom = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(1.0 / o.g[0]));
-            else if (o.type == OT_TILT) m.geom = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], 0.f);
-            else m.geom = make_float4((float)o.g[4], 0.f, 0.f, 0.f);
-            mats[i] = m;
-        }
-        UP_CUDA(cudaMalloc(&ctx->d_mats, sizeof(MatF32) * n));
-        UP_CUDA(cudaMemcpy(ctx->d_mats, mats.data(), sizeof(MatF32) * n, cudaMemcpyHostToDevice));
-    }
-#undef UP_CUDA
+    int rc = upload_tables(ctx);
+    if (rc != PT_OK) { std::string msg = ctx->err; pt_destroy(ctx); return pt_fail(nullptr, rc, msg); }
     *out = ctx;
     return PT_OK;
 }
@@ -249,14 +283,25 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     const pt_render_params &p = ctx->last;
     const size_t n = (size_t)p.width * p.height * 3;
+    if ((rgb_mean || rgb_sumsq) && ctx->stage_elems < n) {      // pinned staging: D2H at full PCIe rate
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->stage_elems = 0;
+        PT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, n * sizeof(double)));
+        ctx->stage_elems = n;
+    }
     if (rgb_mean) {
         const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
-        PT_CUDA(ctx, cudaMemcpy(rgb_mean, src, n * sizeof(double), cudaMemcpyDeviceToHost));
-        if (p.spp > 0) for (size_t i = 0; i < n; i++) rgb_mean[i] = rgb_mean[i] / p.spp;
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const double *hs = ctx->h_stage;
+        if (p.spp > 0) for (size_t i = 0; i < n; i++) rgb_mean[i] = hs[i] / p.spp;
+        else std::memcpy(rgb_mean, hs, n * sizeof(double));
     }
     if (rgb_sumsq) {
         if (!p.collect_stats) return pt_fail(ctx, PT_ERR_STATE, "sum of squares requested but collect_stats was 0");
-        PT_CUDA(ctx, cudaMemcpy(rgb_sumsq, ctx->d_sumsq, n * sizeof(double), cudaMemcpyDeviceToHost));
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, ctx->d_sumsq, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::memcpy(rgb_sumsq, ctx->h_stage, n * sizeof(double));
     }
     if (stats) *stats = ctx->stats;
     return PT_OK;
@@ -351,6 +396,7 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev_batch[0]) cudaEventDestroy(ctx->ev_batch[0]);
     if (ctx->ev_batch[1]) cudaEventDestroy(ctx->ev_batch[1]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

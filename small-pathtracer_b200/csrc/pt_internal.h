@@ -49,7 +49,8 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
 struct MatF32 {                   // global memory (indexed by the hit id: divergent, so NOT constant)
     float4 c_refl;                // c.xyz, refl (int bits)
     float4 e_type;                // e.xyz, type (int bits)
-    float4 geom;                  // sphere: centre.xyz, 1/rad ; rect: k,-,-,- ; tilted: n.xyz
+    float4 geom;                  // sphere: centre.xyz, 1/rad ; rect: k_hi, k_lo (k = hi + lo), -, - ; tilted: n.xyz
+    float4 aux;                   // tilted: p0.xyz
 };
 
 struct DevStats {                 // device-side counters (unsigned long long for atomicAdd)
@@ -68,6 +69,7 @@ struct pt_ctx {
     pt_camera cam{};
     pt_light light{};
     DevObj64 *d_objs = nullptr;
+    int n_alloc = 0;                   // objects d_objs / d_mats can hold
     SceneF32 *h_scene32 = nullptr;     // host staging copy (heap; copied to __constant__ before FP32 launches)
     MatF32 *d_mats = nullptr;
     bool fp32_ok = false;              // scene fits the FP32 constant layout
@@ -89,6 +91,8 @@ struct pt_ctx {
     unsigned int *h_pinned = nullptr;                  // 2 pinned words for the termination check
     cudaEvent_t ev_batch[2] = {nullptr, nullptr};
     DevStats *h_stats = nullptr;                       // pinned
+    double *h_stage = nullptr;                         // pinned staging for pt_readback
+    size_t stage_elems = 0;
     DevStats *d_stats = nullptr;
     pt_stats stats{};
     std::string err;

@@ -153,15 +153,36 @@ __device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, 
     id_out = bid;
 }
 
-// hittingPoint (:371-377) for the winning object.  Rectangles: t and the plane coordinate are recomputed
-// with IEEE division and separate multiply/add — the reference's own forms — so that the distribution
-// of "exactly on / just in front of / just behind the plane" (which drives its self-hit leaks) carries over.
-__device__ __forceinline__ F3 hit_point(F3 o, F3 d, float t, int type, float k)
+// hittingPoint (:371-377) for the winning object, with t refined once (the loop's t is rcp/approx-sqrt based).
+// Rectangles: t and the plane coordinate are recomputed with IEEE division and separate multiply/add — the
+// reference's own forms — so that the distribution of "exactly on / just in front of / just behind the plane"
+// (which drives its self-hit leaks) carries over; the plane constant is a two-float (hi + lo) so t keeps
+// ~1e-7 relative accuracy even where FP32 cannot represent k (81.6, 81.5).
+// Small spheres: one Newton step on |o + d t - c|^2 = r^2 from the hit point (numbers near the surface are
+// small, so the residual is accurate where the quadratic's coefficients were not).
+__device__ __forceinline__ float refine_t(F3 o, F3 d, float t, int type, float4 geom, float4 aux)
+{
+    if (type == OT_XZ) return __fdiv_rn((geom.x - o.y) + geom.y, d.y);
+    if (type == OT_XY) return __fdiv_rn((geom.x - o.z) + geom.y, d.z);
+    if (type == OT_YZ) return __fdiv_rn((geom.x - o.x) + geom.y, d.x);
+    if (type == OT_TILT)       // n.(p0 - o) / n.d with the difference taken first and IEEE division
+        return __fdiv_rn(dot3(f3(geom.x, geom.y, geom.z), f3(aux.x - o.x, aux.y - o.y, aux.z - o.z)), dot3(f3(geom.x, geom.y, geom.z), d));
+    if (type == OT_SPHERE && geom.w > (1.f / (float)PT_HUGE_RADIUS)) {
+        const float rad = 1.f / geom.w;
+        F3 r = f3(fmaf(d.x, t, o.x) - geom.x, fmaf(d.y, t, o.y) - geom.y, fmaf(d.z, t, o.z) - geom.z);
+        const float f = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, -rad * rad)));
+        const float g = 2.f * dot3(r, d);
+        if (fabsf(g) > 1e-3f * rad) t -= f / g;
+    }
+    return t;
+}
+
+__device__ __forceinline__ F3 hit_point(F3 o, F3 d, float t, int type)
 {
     F3 x = fma3(d, t, o);
-    if (type == OT_XZ) { float te = __fdiv_rn(k - o.y, d.y); x = fma3(d, te, o); x.y = __fadd_rn(o.y, __fmul_rn(d.y, te)); }
-    else if (type == OT_XY) { float te = __fdiv_rn(k - o.z, d.z); x = fma3(d, te, o); x.z = __fadd_rn(o.z, __fmul_rn(d.z, te)); }
-    else if (type == OT_YZ) { float te = __fdiv_rn(k - o.x, d.x); x = fma3(d, te, o); x.x = __fadd_rn(o.x, __fmul_rn(d.x, te)); }
+    if (type == OT_XZ) x.y = __fadd_rn(o.y, __fmul_rn(d.y, t));
+    else if (type == OT_XY) x.z = __fadd_rn(o.z, __fmul_rn(d.z, t));
+    else if (type == OT_YZ) x.x = __fadd_rn(o.x, __fmul_rn(d.x, t));
     return x;
 }
 
@@ -264,7 +285,7 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
         else on_obj = id;
         const MatF32 m = P.mats[id];
         const int type = __float_as_int(m.e_type.w), refl = __float_as_int(m.c_refl.w);
-        if (on_obj >= 0) x = hit_point(o, d, t, type, m.geom.x);
+        if (on_obj >= 0) { t = refine_t(o, d, t, type, m.geom, m.aux); x = hit_point(o, d, t, type); }
         // ---- normal(), :118-124 / :246-253
         F3 ng;
         if (type == OT_SPHERE) ng = f3(x.x - m.geom.x, x.y - m.geom.y, x.z - m.geom.z) * m.geom.w;
@@ -487,12 +508,9 @@ __global__ void k_intersect_fp32(const double *__restrict__ rays, int n_rays, do
     float t; int id;
     closest_hit(o, d, -1, t, id);
     if (id >= 0) {
-        // report the t the shading stage uses (exact-division form for rectangles)
+        // report the t the shading stage uses (refined once for the winning object)
         const MatF32 m = mats[id];
-        const int type = __float_as_int(m.e_type.w);
-        if (type == OT_XZ) t = __fdiv_rn(m.geom.x - o.y, d.y);
-        else if (type == OT_XY) t = __fdiv_rn(m.geom.x - o.z, d.z);
-        else if (type == OT_YZ) t = __fdiv_rn(m.geom.x - o.x, d.x);
+        t = refine_t(o, d, t, __float_as_int(m.e_type.w), m.geom, m.aux);
     }
     t_out[i] = id >= 0 ? (double)t : 1e20;
     id_out[i] = id;

@@ -40,11 +40,10 @@ def test_gate2_three_sigma_vs_converged_reference(scene, mode):
     frac = outside.sum() / max(1, informative.sum())
     assert frac <= 0.01, f"{100 * frac:.3f} % of pixel-channels beyond 3 sigma"
     assert np.abs(mean[~informative] - omean[~informative]).max(initial=0) < 1e-3
-    # no global bias beyond 1 % over the well-converged pixels (the reference's NEE has a heavy 1/t^2 tail near the
-    # light, so the raw image mean is dominated by a handful of fireflies); same work per path as the reference
-    conv = informative & (se < 0.05 * np.maximum(omean, 1e-6))
-    assert conv.mean() > 0.5
-    assert abs((mean[conv] - omean[conv]).sum()) < 0.01 * omean[conv].sum()
+    # no global bias: the summed difference stays within 1 % of the image plus 4 standard errors of the sum (the
+    # reference's NEE has a heavy 1/t^2 tail near the light, which the per-pixel variances carry)
+    tot_diff, tot_se = (mean - omean).sum(), np.sqrt((se ** 2).sum())
+    assert abs(tot_diff) < 0.01 * omean.sum() + 4 * tot_se, (tot_diff / omean.sum(), tot_se / omean.sum())
     assert abs(st.rays / st.paths - float(ref["rays_per_path"])) < 0.03 * float(ref["rays_per_path"])
     assert st.truncated == 0 and st.paths == w * h * spp
 
@@ -87,25 +86,39 @@ def test_sharded_image_is_bit_identical(world, tile):
     assert np.array_equal(total, full)
 
 
-def test_cone_light_sampling_is_unbiased_on_scene_B():
-    # NEE_CONE_SPHERE is not in the reference source; it must share its expectation with the reference's
-    # (unbiased) cosine mode on the sphere-era scene, and have lower variance.
+def _scene_B_with_light(rad, centre, emission, w, h):
+    base = ptb.builtin_scene("B", w, h)
+    spheres = [base.spheres[i] for i in range(9)] + [ptb.sphere(rad, centre, e=(emission,) * 3, c=(0, 0, 0))]
+    return ptb.Scene(spheres, [], [~i for i in range(10)], base.light, base.camera)
+
+
+@pytest.mark.parametrize("light", ["builtin", "small"])
+def test_cone_light_sampling_is_unbiased(light):
+    # NEE_CONE_SPHERE is not in the reference source (parity unpinned); it must share its expectation with the
+    # reference's (unbiased) cosine mode.  "builtin": the sphere-era scene (a 600-radius light mostly hidden above
+    # the ceiling); "small": the classic 1.5-radius light of Beason's explicit.cpp, where cone sampling must also
+    # cut the variance by a large factor.
     w = h = 64
-    sc = ptb.builtin_scene("B", w, h)
+    if light == "builtin":
+        sc, n_cone, n_cos = ptb.builtin_scene("B", w, h), 2048, 4096
+    else:
+        sc, n_cone, n_cos = _scene_B_with_light(1.5, (50, 81.6 - 16.5, 81.6), 400.0, w, h), 1024, 16384
     with ptb.Context(sc) as c:
-        c.render(ptb.params(w, h, 2048, mode=ptb.PT_MODE_NEE_CONE_SPHERE, seed=1, collect_stats=1))
+        c.render(ptb.params(w, h, n_cone, mode=ptb.PT_MODE_NEE_CONE_SPHERE, seed=1, collect_stats=1))
         m_cone, s_cone, st_cone = c.readback(True)
-        c.render(ptb.params(w, h, 4096, mode=ptb.PT_MODE_COS, seed=2, collect_stats=1))
+        c.render(ptb.params(w, h, n_cos, mode=ptb.PT_MODE_COS, seed=2, collect_stats=1))
         m_cos, s_cos, st_cos = c.readback(True)
-    z, se = z_scores(m_cone, s_cone, 2048, m_cos, s_cos, 4096)
-    # the light sphere itself is seen directly in a few pixels (zero variance there)
+    z, se = z_scores(m_cone, s_cone, n_cone, m_cos, s_cos, n_cos)
     informative = se > 1e-9
     frac = ((np.abs(z) > 3) & informative).sum() / informative.sum()
-    assert frac <= 0.01, frac
-    assert abs(m_cone.mean() - m_cos.mean()) < 0.01 * m_cos.mean()
-    var_cone = np.maximum(s_cone / 2048 - m_cone ** 2, 0).mean()
-    var_cos = np.maximum(s_cos / 4096 - m_cos ** 2, 0).mean()
-    assert var_cone < 0.5 * var_cos
+    assert frac <= 0.012, frac
+    tot_diff, tot_se = (m_cone - m_cos).sum(), np.sqrt((se ** 2).sum())
+    assert abs(tot_diff) < 0.01 * m_cos.sum() + 4 * tot_se
+    if light == "small":
+        indirect = (m_cos < 20).all(axis=2)                 # drop the few pixels that see the 400-bright light directly
+        var_cone = np.maximum(s_cone / n_cone - m_cone ** 2, 0)[indirect].mean()
+        var_cos = np.maximum(s_cos / n_cos - m_cos ** 2, 0)[indirect].mean()
+        assert var_cone < 0.1 * var_cos, (var_cone, var_cos)
 
 
 def test_synthetic_scene_matches_oracle_statistics():
@@ -138,5 +151,8 @@ def test_full_size_c2_properties():
     assert np.array_equal(a, b)
     assert st.paths == 512 * 512 * 512 and st.truncated == 0
     assert abs(st.rays / st.paths - 3.06) < 0.08
-    assert abs(np.clip(a, 0, 1).mean() - 0.283) < 0.004
+    ref = np.load(os.path.join(GOLDEN, "converged_A_nee.npz"))      # same view at 128x128, 4096 spp, FP64 reference algorithm
+    lo = a.reshape(128, 4, 128, 4, 3).mean(axis=(1, 3))             # box-filter the 512x512 image down to 128x128
+    assert abs(lo.mean() - ref["mean"].mean()) < 0.02 * ref["mean"].mean()
+    assert np.median(np.abs(lo - ref["mean"]) / np.maximum(ref["mean"], 1e-3)) < 0.03
     assert np.isfinite(a).all() and (a >= 0).all()
