@@ -17,58 +17,98 @@ int pt_fail(pt_ctx *ctx, int code, const std::string &msg)
 
 static inline bool finite3(const pt_vec3 &v) { return std::isfinite(v.x) && std::isfinite(v.y) && std::isfinite(v.z); }
 
-// Build the FP32 class-sorted constant-memory image of the scene.
-static void build_scene_f32(pt_ctx *ctx)
+// Build the FP32 class-sorted constant-memory image of the scene and the code-indexed material table.
+static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
 {
     SceneF32 &S = *ctx->h_scene32;
     std::memset(&S, 0, sizeof S);
     const int n = (int)ctx->objs.size();
     ctx->fp32_ok = true;
     ctx->fp32_why.clear();
+    mats.clear();
     if (n > PT_MAX_OBJ) { ctx->fp32_ok = false; ctx->fp32_why = "more than 512 objects"; return; }
-    S.n_obj = n;
-    int nr = 0;
+    std::vector<int> code_of(n, -1);
+    // rectangles: the first PT_RECT_SLOTS of each axis class go to the unrolled slots, the rest to the overflow loop
+    int n_ovf = 0;
     for (int axis = 0; axis < 3; axis++) {       // XZ, XY, YZ
-        S.rect_begin[axis] = nr;
+        S.ovf_begin[axis] = n_ovf;
         const int want = axis == 0 ? OT_XZ : axis == 1 ? OT_XY : OT_YZ;
+        int k = 0;
         for (int i = 0; i < n; i++) {
             const DevObj64 &o = ctx->objs[i];
             if (o.type != want) continue;
-            S.rect_a[nr] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
-            S.rect_b[nr] = make_float2((float)o.g[3], 0.f);
-            std::memcpy(&S.rect_b[nr].y, &i, sizeof(int));
-            nr++;
+            if (k < PT_RECT_SLOTS) {
+                S.slot_a[axis][k] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
+                S.slot_b2[axis][k] = (float)o.g[3];
+                code_of[i] = axis * PT_RECT_SLOTS + k;
+                k++;
+            } else {
+                S.rect_a[n_ovf] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
+                S.rect_b2[n_ovf] = (float)o.g[3];
+                code_of[i] = 3 * PT_RECT_SLOTS + n_ovf;
+                n_ovf++;
+            }
         }
+        S.n_slot[axis] = k;
     }
-    S.rect_begin[3] = nr;
+    S.ovf_begin[3] = n_ovf;
+    int n_small = 0, n_huge = 0, n_tilt = 0;
+    for (int i = 0; i < n; i++) {
+        const DevObj64 &o = ctx->objs[i];
+        if (o.type == OT_SPHERE) { if (o.g[0] >= PT_HUGE_RADIUS) n_huge++; else n_small++; }
+        else if (o.type == OT_TILT) n_tilt++;
+    }
+    if (n_huge > PT_MAX_HUGE) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 huge spheres"; return; }
+    if (n_tilt > PT_MAX_TILT) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 tilted planes"; return; }
+    S.code_sph0 = 3 * PT_RECT_SLOTS + n_ovf;
+    S.code_huge0 = S.code_sph0 + n_small;
+    S.code_tilt0 = S.code_huge0 + n_huge;
+    S.n_codes = S.code_tilt0 + n_tilt;
     for (int i = 0; i < n; i++) {
         const DevObj64 &o = ctx->objs[i];
         if (o.type == OT_SPHERE) {
             if (o.g[0] >= PT_HUGE_RADIUS) {
-                if (S.n_huge >= PT_MAX_HUGE) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 huge spheres"; return; }
                 double *h = S.huge[S.n_huge];
                 h[0] = o.g[1]; h[1] = o.g[2]; h[2] = o.g[3]; h[3] = o.g[0] * o.g[0];
-                S.huge_id[S.n_huge++] = i;
+                code_of[i] = S.code_huge0 + S.n_huge++;
             } else {
                 S.sph[S.n_sph] = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(o.g[0] * o.g[0]));
-                S.sph_id[S.n_sph++] = i;
+                code_of[i] = S.code_sph0 + S.n_sph++;
             }
-            if ((o.e[0] > 0 || o.e[1] > 0 || o.e[2] > 0) && S.n_lights < 32) S.light_sph[S.n_lights++] = i;
+            if ((o.e[0] > 0 || o.e[1] > 0 || o.e[2] > 0) && S.n_lights < 32) S.light_sph_code[S.n_lights++] = code_of[i];
         } else if (o.type == OT_TILT) {
-            if (S.n_tilt >= PT_MAX_TILT) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 tilted planes"; return; }
-            float4 *t = S.tilt[S.n_tilt++];
+            float4 *t = S.tilt[S.n_tilt];
             auto dotp = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
             t[0] = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], (float)dotp(o.n, o.p0));
             t[1] = make_float4((float)o.s[0], (float)o.s[1], (float)o.s[2], (float)dotp(o.s, o.p0));
             t[2] = make_float4((float)o.t[0], (float)o.t[1], (float)o.t[2], (float)dotp(o.t, o.p0));
             t[3] = make_float4((float)o.hs, (float)o.ht, 0.f, 0.f);
-            std::memcpy(&t[3].z, &i, sizeof(int));
+            code_of[i] = S.code_tilt0 + S.n_tilt++;
         }
     }
-    S.light_id = ctx->light.id;
+    S.code_obj0 = code_of[0];
+    S.light_code = (ctx->light.id >= 0 && ctx->light.id < n) ? code_of[ctx->light.id] : -2;
     S.lx0 = (float)ctx->light.x0; S.lxw = (float)ctx->light.xw;
     S.lz0 = (float)ctx->light.z0; S.lzw = (float)ctx->light.zw;
     S.ly = (float)ctx->light.y; S.larea = (float)ctx->light.area;
+    // materials by code (unused slots stay zero)
+    MatF32 zero;
+    std::memset(&zero, 0, sizeof zero);
+    mats.assign(S.n_codes, zero);
+    for (int i = 0; i < n; i++) {
+        const DevObj64 &o = ctx->objs[i];
+        MatF32 m;
+        m.c_refl = make_float4((float)o.c[0], (float)o.c[1], (float)o.c[2], 0.f);
+        std::memcpy(&m.c_refl.w, &o.refl, sizeof(int));
+        m.e_type = make_float4((float)o.e[0], (float)o.e[1], (float)o.e[2], 0.f);
+        std::memcpy(&m.e_type.w, &o.type, sizeof(int));
+        m.aux = make_float4((float)o.p0[0], (float)o.p0[1], (float)o.p0[2], 0.f);
+        std::memcpy(&m.aux.w, &i, sizeof(int));
+        if (o.type == OT_SPHERE) m.geom = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(1.0 / o.g[0]));
+        else if (o.type == OT_TILT) m.geom = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], 0.f);
+        else { const float khi = (float)o.g[4]; m.geom = make_float4(khi, (float)(o.g[4] - (double)khi), 0.f, 0.f); }
+        mats[code_of[i]] = m;
+    }
 }
 
 extern "C" {
@@ -118,29 +158,23 @@ static int upload_tables(pt_ctx *ctx)
     const int n = (int)ctx->objs.size();
     if (ctx->n_alloc < n) {
         if (ctx->d_objs) cudaFree(ctx->d_objs);
-        if (ctx->d_mats) cudaFree(ctx->d_mats);
-        ctx->d_objs = nullptr; ctx->d_mats = nullptr; ctx->n_alloc = 0;
+        ctx->d_objs = nullptr; ctx->n_alloc = 0;
         PT_CUDA(ctx, cudaMalloc(&ctx->d_objs, sizeof(DevObj64) * n));
-        PT_CUDA(ctx, cudaMalloc(&ctx->d_mats, sizeof(MatF32) * n));
         ctx->n_alloc = n;
     }
-    build_scene_f32(ctx);
-    std::vector<MatF32> mats(n);
-    for (int i = 0; i < n; i++) {
-        const DevObj64 &o = ctx->objs[i];
-        MatF32 m;
-        m.c_refl = make_float4((float)o.c[0], (float)o.c[1], (float)o.c[2], 0.f);
-        std::memcpy(&m.c_refl.w, &o.refl, sizeof(int));
-        m.e_type = make_float4((float)o.e[0], (float)o.e[1], (float)o.e[2], 0.f);
-        std::memcpy(&m.e_type.w, &o.type, sizeof(int));
-        m.aux = make_float4((float)o.p0[0], (float)o.p0[1], (float)o.p0[2], 0.f);
-        if (o.type == OT_SPHERE) m.geom = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(1.0 / o.g[0]));
-        else if (o.type == OT_TILT) m.geom = make_float4((float)o.n[0], (float)o.n[1], (float)o.n[2], 0.f);
-        else { const float khi = (float)o.g[4]; m.geom = make_float4(khi, (float)(o.g[4] - (double)khi), 0.f, 0.f); }
-        mats[i] = m;
-    }
+    std::vector<MatF32> mats;
+    build_scene_f32(ctx, mats);
     PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_objs, ctx->objs.data(), sizeof(DevObj64) * n, cudaMemcpyHostToDevice, ctx->stream));
-    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), sizeof(MatF32) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->fp32_ok) {
+        const int nc = (int)mats.size();
+        if (ctx->n_codes_alloc < nc) {
+            if (ctx->d_mats) cudaFree(ctx->d_mats);
+            ctx->d_mats = nullptr; ctx->n_codes_alloc = 0;
+            PT_CUDA(ctx, cudaMalloc(&ctx->d_mats, sizeof(MatF32) * nc));
+            ctx->n_codes_alloc = nc;
+        }
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), sizeof(MatF32) * nc, cudaMemcpyHostToDevice, ctx->stream));
+    }
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PT_OK;
 }

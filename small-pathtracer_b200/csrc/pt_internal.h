@@ -28,29 +28,39 @@ struct DevObj64 {
 #define PT_MAX_TILT       64
 #define PT_HUGE_RADIUS    100.0   // spheres at least this big take the FP64 c-term path
 
+#define PT_RECT_SLOTS     16      // rectangles per axis class tested by fully unrolled, constant-operand code
+
+// The FP32 engine addresses objects by CODE (position in the class-sorted layout), not by scene id:
+//   [0, 48)                         unrolled rectangle slots, code = axis*16 + k   (axis: XZ 0, XY 1, YZ 2)
+//   [48, 48 + n_ovf)                overflow rectangles (generic loop), axis by axis
+//   [code_sph0, +n_sph)             small spheres        [code_huge0, +n_huge)  huge spheres
+//   [code_tilt0, +n_tilt)           tilted planes
+// Within a class codes ascend with scene id, so "lowest id wins ties" (src/smallpt.cpp:328) holds per class.
 struct SceneF32 {                 // lives in __constant__ memory: every access is warp-uniform
-    int   n_obj;
-    int   rect_begin[4];          // [axis] .. [axis+1): entries of rect_* for XZ(0), XY(1), YZ(2)
+    int   n_slot[3];              // rectangles in the unrolled slots of each axis class (<= PT_RECT_SLOTS)
+    int   ovf_begin[4];           // [axis] .. [axis+1): overflow entries of rect_a / rect_b2
     int   n_sph, n_huge, n_tilt;
+    int   code_sph0, code_huge0, code_tilt0, n_codes;
+    int   code_obj0;              // code of scene object 0 (where a missed ray "lands", :373-374)
     // NEE_REF_RECT light (src/smallpt.cpp:365-367,467,471)
-    int   light_id;
+    int   light_code;
     float lx0, lxw, lz0, lzw, ly, larea;
     int   n_lights;               // emissive spheres for NEE_CONE_SPHERE
-    int   light_sph[32];          // object ids
-    float4 rect_a[PT_MAX_OBJ];    // k, a1, a2, b1
-    float2 rect_b[PT_MAX_OBJ];    // b2, id (int bits)
+    int   light_sph_code[32];
+    float4 slot_a[3][PT_RECT_SLOTS];   // k, a1, a2, b1   (one 128-bit uniform load)
+    float  slot_b2[3][PT_RECT_SLOTS];  // b2
+    float4 rect_a[PT_MAX_OBJ];    // overflow rectangles: k, a1, a2, b1
+    float  rect_b2[PT_MAX_OBJ];   //                      b2
     float4 sph[PT_MAX_OBJ];       // c.x, c.y, c.z, rad^2
-    int    sph_id[PT_MAX_OBJ];
     double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64
-    int    huge_id[PT_MAX_HUGE];
-    float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, id, -}
+    float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
 };
 
-struct MatF32 {                   // global memory (indexed by the hit id: divergent, so NOT constant)
+struct MatF32 {                   // global memory, indexed by CODE (divergent index, so NOT constant memory)
     float4 c_refl;                // c.xyz, refl (int bits)
     float4 e_type;                // e.xyz, type (int bits)
     float4 geom;                  // sphere: centre.xyz, 1/rad ; rect: k_hi, k_lo (k = hi + lo), -, - ; tilted: n.xyz
-    float4 aux;                   // tilted: p0.xyz
+    float4 aux;                   // tilted: p0.xyz ; .w = scene id (int bits)
 };
 
 struct DevStats {                 // device-side counters (unsigned long long for atomicAdd)
@@ -71,7 +81,8 @@ struct pt_ctx {
     DevObj64 *d_objs = nullptr;
     int n_alloc = 0;                   // objects d_objs / d_mats can hold
     SceneF32 *h_scene32 = nullptr;     // host staging copy (heap; copied to __constant__ before FP32 launches)
-    MatF32 *d_mats = nullptr;
+    MatF32 *d_mats = nullptr;          // indexed by code
+    int n_codes_alloc = 0;
     bool fp32_ok = false;              // scene fits the FP32 constant layout
     std::string fp32_why;
     // render state

@@ -50,6 +50,8 @@ struct KParams {
     unsigned int owned_pixels;
     double inv_owned_pixels;
     int w, h, spp, tile_rows, rank, world, max_depth;
+    unsigned long long magic_w, magic_tile;   // ceil(2^40 / w), ceil(2^40 / tile_rows): exact n / d for n < 2^24, d < 2^16
+    int use_magic;                     // owned_pixels < 2^24
     float cam_o[3], cam_base[3], cam_h[3], cam_v[3];   // origin, llc - origin, horizontal, vertical
     float inv_w, inv_h;
     unsigned int seed_lo, seed_hi;
@@ -73,37 +75,59 @@ __device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.f3
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ---------------------------------------------------------------------------------------------- extend
-// One axis class of the reference's rectangles (:102-112 / :145-155 / :188-198): t = (k - o_a) / d_a, the
-// two in-plane coordinates against [a1,a2] x [b1,b2], NO epsilon, t == 0 and t < 0 are misses.
-__device__ __forceinline__ void rects_axis(int begin, int end, float oa, float ia, float ou, float du, float ov, float dv,
-                                           float &best, int &bid)
+// One rectangle of the reference (:102-112 / :145-155 / :188-198): t = (k - o_a) / d_a, the two in-plane
+// coordinates against [a1,a2] x [b1,b2], NO epsilon, t == 0 and t < 0 are misses.  AX and K are compile-time, so
+// every scene constant is a constant-bank operand of the arithmetic instruction itself (no loads, no loop).
+// Slots are visited in DESCENDING k with `t <= best`, which keeps the lowest id on ties like the strict `<`
+// of the ascending loop at :328.
+template <int AX, int K>
+__device__ __forceinline__ void rect_slot(float oa, float ia, float ou, float du, float ov, float dv, float &best, int &code)
 {
-    for (int i = begin; i < end; i++) {
+    const float4 ra = c_scene.slot_a[AX][K];
+    const float t = (ra.x - oa) * ia;
+    const float u = fmaf(du, t, ou), v = fmaf(dv, t, ov);
+    const bool ok = !(u < ra.y) && !(u > ra.z) && !(v < ra.w) && !(v > c_scene.slot_b2[AX][K]) && (t > 0.f) && (t <= best);
+    if (ok) { best = t; code = AX * PT_RECT_SLOTS + K; }
+}
+
+#define PT_SLOT_CASE(K) case K + 1: rect_slot<AX, K>(oa, ia, ou, du, ov, dv, best, code); /* fall through */
+
+template <int AX>
+__device__ __forceinline__ void rects_axis(float oa, float ia, float ou, float du, float ov, float dv, float &best, int &code)
+{
+    switch (c_scene.n_slot[AX]) {          // warp-uniform jump into the unrolled sequence (Duff's device)
+        PT_SLOT_CASE(15) PT_SLOT_CASE(14) PT_SLOT_CASE(13) PT_SLOT_CASE(12) PT_SLOT_CASE(11) PT_SLOT_CASE(10) PT_SLOT_CASE(9)
+        PT_SLOT_CASE(8) PT_SLOT_CASE(7) PT_SLOT_CASE(6) PT_SLOT_CASE(5) PT_SLOT_CASE(4) PT_SLOT_CASE(3) PT_SLOT_CASE(2)
+        PT_SLOT_CASE(1) PT_SLOT_CASE(0)
+    default: break;
+    }
+    // overflow rectangles of this axis class (more than PT_RECT_SLOTS): generic loop, ascending, strict <
+    for (int i = c_scene.ovf_begin[AX]; i < c_scene.ovf_begin[AX + 1]; i++) {
         const float4 ra = c_scene.rect_a[i];
-        const float2 rb = c_scene.rect_b[i];
-        float t = (ra.x - oa) * ia;
-        float u = fmaf(du, t, ou), v = fmaf(dv, t, ov);
-        bool ok = !(u < ra.y) && !(u > ra.z) && !(v < ra.w) && !(v > rb.x) && (t > 0.f) && (t < best);
-        if (ok) { best = t; bid = __float_as_int(rb.y); }
+        const float t = (ra.x - oa) * ia;
+        const float u = fmaf(du, t, ou), v = fmaf(dv, t, ov);
+        const bool ok = !(u < ra.y) && !(u > ra.z) && !(v < ra.w) && !(v > c_scene.rect_b2[i]) && (t > 0.f) && (t < best);
+        if (ok) { best = t; code = 3 * PT_RECT_SLOTS + i; }
     }
 }
 
-// intersect(Ray,t,id), :323-335.  prev = id of the object the ray starts on (-1: none).
-// Returns best t (1e20f on a miss) and id (-1 on a miss).
-__device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, int &id_out)
+// intersect(Ray,t,id), :323-335.  prev = code of the object the ray starts on (-1: none).
+// Returns best t (1e20f on a miss) and the winner's code (-1 on a miss).
+__device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, int &code_out)
 {
     float best = 1e20f;
-    int bid = -1;
+    int code = -1;
     const float ix = rcp_fast(d.x), iy = rcp_fast(d.y), iz = rcp_fast(d.z);
-    rects_axis(c_scene.rect_begin[0], c_scene.rect_begin[1], o.y, iy, o.x, d.x, o.z, d.z, best, bid);   // XZ: plane y
-    rects_axis(c_scene.rect_begin[1], c_scene.rect_begin[2], o.z, iz, o.x, d.x, o.y, d.y, best, bid);   // XY: plane z
-    rects_axis(c_scene.rect_begin[2], c_scene.rect_begin[3], o.x, ix, o.y, d.y, o.z, d.z, best, bid);   // YZ: plane x
+    rects_axis<0>(o.y, iy, o.x, d.x, o.z, d.z, best, code);   // XZ: plane y
+    rects_axis<1>(o.z, iz, o.x, d.x, o.y, d.y, best, code);   // XY: plane z
+    rects_axis<2>(o.x, ix, o.y, d.y, o.z, d.z, best, code);   // YZ: plane x
 
     // Sphere::intersect, :229-239, eps = 1e-4.  det = r^2 - |op - b d|^2 (perpendicular distance form).
     const int ns = c_scene.n_sph;
+    const int prev_s = prev - c_scene.code_sph0;
+#pragma unroll 4
     for (int i = 0; i < ns; i++) {
         const float4 s = c_scene.sph[i];
-        const int sid = c_scene.sph_id[i];
         F3 op = f3(s.x - o.x, s.y - o.y, s.z - o.z);
         float b = dot3(op, d);
         F3 l = f3(fmaf(-b, d.x, op.x), fmaf(-b, d.y, op.y), fmaf(-b, d.z, op.z));
@@ -112,19 +136,19 @@ __device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, 
             float sq = sqrt_fast(det);
             float t0 = b - sq, t1 = b + sq;
             float tt = t0 > PT_EPS_F ? t0 : t1;
-            if (sid == prev) tt = b + b;          // origin on this sphere: roots are exactly {0, 2b}
-            if (tt > PT_EPS_F && tt < best) { best = tt; bid = sid; }
+            if (i == prev_s) tt = b + b;          // origin on this sphere: roots are exactly {0, 2b}
+            if (tt > PT_EPS_F && tt < best) { best = tt; code = c_scene.code_sph0 + i; }
         }
     }
     // Huge spheres (the 1e5-radius walls of the sphere-era scene): c in FP64, conjugate roots in FP32.
     const int nh = c_scene.n_huge;
     if (nh > 0) {
         const double ox = (double)o.x, oy = (double)o.y, oz = (double)o.z;
+        const int prev_h = prev - c_scene.code_huge0;
         for (int i = 0; i < nh; i++) {
-            const int sid = c_scene.huge_id[i];
             double px = c_scene.huge[i][0] - ox, py = c_scene.huge[i][1] - oy, pz = c_scene.huge[i][2] - oz;
             double c64 = fma(px, px, fma(py, py, fma(pz, pz, -c_scene.huge[i][3])));
-            float c = (sid == prev) ? 0.f : (float)c64;
+            float c = (i == prev_h) ? 0.f : (float)c64;
             float b = dot3(f3((float)px, (float)py, (float)pz), d);
             float det = fmaf(b, b, -c);
             if (det >= 0.f) {
@@ -132,7 +156,7 @@ __device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, 
                 float ta = q, tb = c * rcp_fast(q);
                 float lo = fminf(ta, tb), hi = fmaxf(ta, tb);
                 float tt = lo > PT_EPS_F ? lo : hi;
-                if (tt > PT_EPS_F && tt < best) { best = tt; bid = sid; }
+                if (tt > PT_EPS_F && tt < best) { best = tt; code = c_scene.code_huge0 + i; }
             }
         }
     }
@@ -147,10 +171,10 @@ __device__ __forceinline__ void closest_hit(F3 o, F3 d, int prev, float &t_out, 
         float a = fmaf(ps.x, hp.x, fmaf(ps.y, hp.y, ps.z * hp.z)) - ps.w;
         float b = fmaf(pt.x, hp.x, fmaf(pt.y, hp.y, pt.z * hp.z)) - pt.w;
         bool ok = (fabsf(a) <= pe.x) && (fabsf(b) <= pe.y) && (tau > PT_EPS_F) && (tau < best);
-        if (ok) { best = tau; bid = __float_as_int(pe.z); }
+        if (ok) { best = tau; code = c_scene.code_tilt0 + i; }
     }
     t_out = best;
-    id_out = bid;
+    code_out = code;
 }
 
 // hittingPoint (:371-377) for the winning object, with t refined once (the loop's t is rcp/approx-sqrt based).
@@ -216,49 +240,27 @@ __device__ __forceinline__ unsigned int pack_state(int depth, int prev, int E)
     return (unsigned int)depth | ((unsigned int)(prev + 1) << 16) | ((unsigned int)E << 31);
 }
 
-// Block-wide exclusive scan of a 0/1 flag + one atomic on *counter by thread 0.  Returns this thread's
-// global slot (base + rank) and the block total.  `smem` = 10 words.
-template <typename CT>
-__device__ __forceinline__ CT block_reserve(bool flag, CT *counter, unsigned int *smem_counts, CT *smem_base, unsigned int &block_total)
-{
-    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, flag);
-    const unsigned int rank_in_warp = __popc(ballot & ((1u << lane) - 1u));
-    if (lane == 0) smem_counts[warp] = __popc(ballot);
-    __syncthreads();
-    unsigned int before = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < PT_BLOCK / 32; i++) {
-        unsigned int c = smem_counts[i];
-        before += (i < (int)warp) ? c : 0u;
-        total += c;
-    }
-    if (threadIdx.x == 0) *smem_base = total ? atomicAdd(counter, (CT)total) : (CT)0;
-    __syncthreads();
-    block_total = total;
-    return *smem_base + before + rank_in_warp;
-}
-
 // ---------------------------------------------------------------------------------------------- the bounce kernel
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
+__global__ void __launch_bounds__(PT_BLOCK, 4) k_bounce(const KParams P)
 {
-    __shared__ unsigned int s_counts[PT_BLOCK / 32];
-    __shared__ unsigned int s_base32;
-    __shared__ unsigned long long s_base64;
-    __shared__ unsigned int s_stat[6];   // shadow, miss, truncated, inline light vertices, scatter, max depth
+    __shared__ unsigned int s_alive[PT_BLOCK / 32], s_want[PT_BLOCK / 32];
+    __shared__ unsigned int s_base_out, s_regen_ok;
+    __shared__ unsigned long long s_base_gen;
+    __shared__ unsigned int s_stat[6];   // shadow, miss, truncated, shaded (+inline), scatter, max depth
 
     const unsigned int tid = blockIdx.x * PT_BLOCK + threadIdx.x;
     const unsigned int n_in = *P.n_in;
     if (blockIdx.x * PT_BLOCK >= n_in) return;          // whole block beyond the queue
     if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
+    __syncthreads();
     const bool have = tid < n_in;
 
     F3 o = f3(0, 0, 0), d = f3(0, 0, 1), T = f3(0, 0, 0), L = f3(0, 0, 0);
     unsigned int pix = 0, smp = 0;
     int depth = 0, prev = -1, E = 1;
     bool alive = false;
-    unsigned int n_shadow = 0, n_miss = 0, n_trunc = 0, n_inline = 0, n_scatter = 0, n_shaded = 0, my_depth = 0;
+    unsigned int n_shadow = 0, n_miss = 0, n_trunc = 0, n_inline = 0, n_shaded = 0, my_depth = 0;
 
     if (have) {
         const float4 c = P.qin[2][tid];
@@ -276,16 +278,16 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
 
     if (alive) {
         // ---- extend: closest hit (:323-335) + hittingPoint (:371-377)
-        float t; int id;
+        float t; int code;
         n_shaded = 1;
-        closest_hit(o, d, prev, t, id);
+        closest_hit(o, d, prev, t, code);
         F3 x;
-        int on_obj;
-        if (id < 0) { x = f3(0.f, 0.f, 0.f); id = 0; on_obj = -1; n_miss++; }          // :373-374: continue from (0,0,0) on object 0
-        else on_obj = id;
-        const MatF32 m = P.mats[id];
+        int on_code;
+        if (code < 0) { x = f3(0.f, 0.f, 0.f); code = c_scene.code_obj0; on_code = -1; n_miss++; }   // :373-374: continue from (0,0,0) on object 0
+        else on_code = code;
+        const MatF32 m = P.mats[code];
         const int type = __float_as_int(m.e_type.w), refl = __float_as_int(m.c_refl.w);
-        if (on_obj >= 0) { t = refine_t(o, d, t, type, m.geom, m.aux); x = hit_point(o, d, t, type); }
+        if (on_code >= 0) { t = refine_t(o, d, t, type, m.geom, m.aux); x = hit_point(o, d, t, type); }
         // ---- normal(), :118-124 / :246-253
         F3 ng;
         if (type == OT_SPHERE) ng = f3(x.x - m.geom.x, x.y - m.geom.y, x.z - m.geom.z) * m.geom.w;
@@ -300,13 +302,15 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
         if (e.x > 0.f || e.y > 0.f || e.z > 0.f) {
             if (STATS) L = L + T * e; else accum_add(P.fix, pix, T * e);
         }
-        // ---- Russian roulette, :447-454
+        // ---- Russian roulette, :447-454.  One Philox block per vertex: x -> RR (high 16 bits) and the REFR
+        // branch (low 16 bits); y, z -> the two sampling uniforms of the first decision (light point or
+        // hemisphere); w and the unused low bytes of y, z, w -> the hemisphere sample after an occluded light.
         const float p = f.x > f.y && f.x > f.z ? f.x : f.y > f.z ? f.y : f.z;
         depth++;
         my_depth = depth;
         const uint4 ra = philox4x32_10(pix, smp, (unsigned)depth, PT_DRAW_A, P.seed_lo, P.seed_hi);
         if (depth > 5 || p == 0.f) {
-            if (u01(ra.x) < p) f = f * (1.f / p);
+            if ((float)(ra.x >> 16) * (1.f / 65536.f) < p) f = f * (1.f / p);
             else alive = false;
         }
         if (alive && depth >= P.max_depth) { alive = false; n_trunc++; }
@@ -317,14 +321,14 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
                     // light_sampling (:363-369) + shadow ray (:466-467)
                     const float xl = fmaf(c_scene.lxw, u01(ra.y), c_scene.lx0), zl = fmaf(c_scene.lzw, u01(ra.z), c_scene.lz0);
                     F3 dl = normalize3(f3(xl - x.x, c_scene.ly - x.y, zl - x.z));
-                    float ts; int ids;
+                    float ts; int cs;
                     n_shadow++;
-                    closest_hit(x, dl, on_obj, ts, ids);
-                    if (ids == c_scene.light_id) {
+                    closest_hit(x, dl, on_code, ts, cs);
+                    if (cs == c_scene.light_code) {
                         const float pdf_inv = fabsf(c_scene.larea * dl.y / (ts * ts));   // :471
                         const float brdf = fabsf(dot3(dl, nl) * PT_INV_PI_F);            // :472
                         T = T * f * (pdf_inv * brdf);
-                        const MatF32 ml = P.mats[ids];
+                        const MatF32 ml = P.mats[cs];
                         const F3 fl = f3(ml.c_refl.x, ml.c_refl.y, ml.c_refl.z);
                         if (fl.x == 0.f && fl.y == 0.f && fl.z == 0.f) {
                             // the path continues along the shadow ray and ends on the (black-bodied) light:
@@ -338,8 +342,8 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
                             dn = dl;       // general light with albedo: keep tracing from here next bounce
                         }
                     } else {
-                        const uint4 rb = philox4x32_10(pix, smp, (unsigned)depth, PT_DRAW_B, P.seed_lo, P.seed_hi);
-                        dn = sample_hemisphere<false>(nl, u01(rb.x), u01(rb.y));          // :468
+                        const unsigned int r2bits = ((ra.y & 0xFFu) << 16) | ((ra.z & 0xFFu) << 8) | (ra.w & 0xFFu);
+                        dn = sample_hemisphere<false>(nl, u01(ra.w), (float)r2bits * (1.0f / 16777216.0f));   // :468
                         T = T * f;
                     }
                     E = 1;
@@ -347,8 +351,8 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
                     dn = sample_hemisphere<false>(nl, u01(ra.y), u01(ra.z));
                     F3 esum = f3(0.f, 0.f, 0.f);
                     for (int li = 0; li < c_scene.n_lights; li++) {
-                        const int lid = c_scene.light_sph[li];
-                        const MatF32 ml = P.mats[lid];
+                        const int lc = c_scene.light_sph_code[li];
+                        const MatF32 ml = P.mats[lc];
                         F3 sw = f3(ml.geom.x - x.x, ml.geom.y - x.y, ml.geom.z - x.z);
                         const float dist2 = dot3(sw, sw), rad = 1.f / ml.geom.w;
                         if (!(dist2 > rad * rad)) continue;
@@ -363,10 +367,10 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
                         float sp, cp;
                         __sincosf(fmaf(2.f * PT_PI_F, eps2, -PT_PI_F), &sp, &cp);
                         F3 l = normalize3(su * (cp * sin_a) + sv * (sp * sin_a) + sw * cos_a);
-                        float ts; int ids;
+                        float ts; int cs;
                         n_shadow++;
-                        closest_hit(x, l, on_obj, ts, ids);
-                        if (ids == lid) {
+                        closest_hit(x, l, on_code, ts, cs);
+                        if (cs == lc) {
                             const float omega = 2.f * PT_PI_F * (1.f - cos_a_max);
                             const float ldn = dot3(l, nl);
                             if (ldn > 0.f) esum = esum + f * f3(ml.e_type.x, ml.e_type.y, ml.e_type.z) * (ldn * omega * PT_INV_PI_F);
@@ -400,11 +404,11 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
                     const float Re = R0 + (1.f - R0) * c * c * c * c * c, Tr = 1.f - Re, Pr = .25f + .5f * Re;
                     // the reference splits into both branches while depth <= 2 (:494-495); a wavefront keeps one
                     // path per slot, so the stochastic branch (:492-493) is used at every depth (same expectation).
-                    if (u01(ra.w) < Pr) { dn = rd; T = T * (Re / Pr); }
+                    if ((float)(ra.x & 0xFFFFu) * (1.f / 65536.f) < Pr) { dn = rd; T = T * (Re / Pr); }
                     else { dn = td; T = T * (Tr / (1.f - Pr)); }
                 }
             }
-            if (alive) { o = x; d = dn; prev = on_obj; n_scatter = 1; }
+            if (alive) { o = x; d = dn; prev = on_code; }
         }
         if (!alive && STATS) {
             // path finished: flush its radiance and its square
@@ -413,23 +417,79 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
         }
     }
 
-    // ---- regeneration: lanes without a live path start the next camera path (:533-536)
-    unsigned int dead_total;
+    // ---- regeneration + compaction in ONE block-wide phase.
+    // Survivors are ranked by warp ballot + block prefix sum; lanes whose path ended ("want") are ranked the same
+    // way and get consecutive new path indices from ONE 64-bit atomic per block; the block's output slots come from
+    // ONE 32-bit atomic per block: survivors first, regenerated paths behind them.
     const bool want = have && !alive;
-    const unsigned long long g = block_reserve<unsigned long long>(want, P.gen_counter, s_counts, &s_base64, dead_total);
-    if (want && g < P.total_paths) {
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int b_alive = __ballot_sync(0xffffffffu, alive), b_want = __ballot_sync(0xffffffffu, want);
+    {   // counters: two warp reductions + a max, folded into the same barrier phase (scatter rays = survivors)
+        const unsigned int pa = n_shadow | (n_miss << 16), pb = n_trunc | ((n_inline + n_shaded) << 16);
+        const unsigned int ra_ = __reduce_add_sync(0xffffffffu, pa), rb_ = __reduce_add_sync(0xffffffffu, pb);
+        const unsigned int md = __reduce_max_sync(0xffffffffu, my_depth);
+        if (lane == 0) {
+            s_alive[warp] = __popc(b_alive); s_want[warp] = __popc(b_want);
+            if (ra_ & 0xFFFFu) atomicAdd(&s_stat[0], ra_ & 0xFFFFu);
+            if (ra_ >> 16) atomicAdd(&s_stat[1], ra_ >> 16);
+            if (rb_ & 0xFFFFu) atomicAdd(&s_stat[2], rb_ & 0xFFFFu);
+            if (rb_ >> 16) atomicAdd(&s_stat[3], rb_ >> 16);
+            atomicMax(&s_stat[5], md);
+        }
+    }
+    __syncthreads();
+    unsigned int alive_before = 0, alive_total = 0, want_before = 0, want_total = 0;
+#pragma unroll
+    for (int i = 0; i < PT_BLOCK / 32; i++) {
+        const unsigned int ca = s_alive[i], cw = s_want[i];
+        alive_before += (i < (int)warp) ? ca : 0u; alive_total += ca;
+        want_before += (i < (int)warp) ? cw : 0u; want_total += cw;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long g0 = 0;
+        unsigned int ok = 0;
+        if (want_total) {
+            g0 = atomicAdd(P.gen_counter, (unsigned long long)want_total);
+            ok = g0 >= P.total_paths ? 0u : (unsigned int)min((unsigned long long)want_total, P.total_paths - g0);
+        }
+        s_base_gen = g0;
+        s_regen_ok = ok;
+        const unsigned int n_out = alive_total + ok;
+        s_base_out = n_out ? atomicAdd(P.n_out, n_out) : 0u;
+        if (s_stat[0]) atomicAdd(&P.stats->rays_shadow, (unsigned long long)s_stat[0]);
+        if (s_stat[1]) atomicAdd(&P.stats->misses, (unsigned long long)s_stat[1]);
+        if (s_stat[2]) atomicAdd(&P.stats->truncated, (unsigned long long)s_stat[2]);
+        if (s_stat[3]) atomicAdd(&P.stats->shaded, (unsigned long long)s_stat[3]);
+        if (alive_total) atomicAdd(&P.stats->rays_scatter, (unsigned long long)alive_total);
+        if (s_stat[5] > 0) atomicMax(&P.stats->max_depth_seen, s_stat[5]);
+    }
+    __syncthreads();
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int rank_alive = alive_before + __popc(b_alive & lt);
+    const unsigned int rank_want = want_before + __popc(b_want & lt);
+    unsigned int slot = s_base_out + rank_alive;
+    if (want && rank_want < s_regen_ok) {
+        // ---- ray generation with uniform sub-pixel jitter (:533-536)
         // path g -> (sample, owned pixel): pixel-major inside a sample so neighbouring lanes are neighbouring pixels
-        unsigned int s = (unsigned int)__double2uint_rz(__ull2double_rz(g) * P.inv_owned_pixels);
-        long long r = (long long)(g - (unsigned long long)s * P.owned_pixels);
-        if (r < 0) { s--; r += P.owned_pixels; }
-        else if (r >= (long long)P.owned_pixels) { s++; r -= P.owned_pixels; }
+        const unsigned long long g = s_base_gen + rank_want;
+        unsigned int sidx = (unsigned int)__double2uint_rz(__ull2double_rz(g) * P.inv_owned_pixels);
+        long long r = (long long)(g - (unsigned long long)sidx * P.owned_pixels);
+        if (r < 0) { sidx--; r += P.owned_pixels; }
+        else if (r >= (long long)P.owned_pixels) { sidx++; r -= P.owned_pixels; }
         const unsigned int lp = (unsigned int)r;
-        const unsigned int row_local = lp / (unsigned int)P.w, xpix = lp - row_local * (unsigned int)P.w;
-        const unsigned int tile = row_local / (unsigned int)P.tile_rows;
+        unsigned int row_local, tile;
+        if (P.use_magic) {               // multiply-shift division (warp-uniform branch)
+            row_local = (unsigned int)(((unsigned long long)lp * P.magic_w) >> 40);
+            tile = (unsigned int)(((unsigned long long)row_local * P.magic_tile) >> 40);
+        } else {
+            row_local = lp / (unsigned int)P.w;
+            tile = row_local / (unsigned int)P.tile_rows;
+        }
+        const unsigned int xpix = lp - row_local * (unsigned int)P.w;
         const unsigned int y = (tile * (unsigned int)P.world + (unsigned int)P.rank) * (unsigned int)P.tile_rows
                              + (row_local - tile * (unsigned int)P.tile_rows);
         pix = y * (unsigned int)P.w + xpix;
-        smp = s;
+        smp = sidx;
         const uint4 rj = philox4x32_10(pix, smp, 0u, PT_DRAW_A, P.seed_lo, P.seed_hi);
         const float u = ((float)xpix - 0.5f + u01(rj.x)) * P.inv_w;                            // :533
         const float v = ((float)(P.h - 1 - (int)y) - 0.5f + u01(rj.y)) * P.inv_h;              // :534
@@ -442,11 +502,8 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
         L = f3(0.f, 0.f, 0.f);
         depth = 0; prev = -1; E = 1;
         alive = true;
+        slot = s_base_out + alive_total + rank_want;
     }
-
-    // ---- compaction: warp ballot + block prefix sum + one atomic per block
-    unsigned int alive_total;
-    const unsigned int slot = block_reserve<unsigned int>(alive, P.n_out, s_counts, &s_base32, alive_total);
     if (alive) {
         P.qout[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(pix));
         P.qout[1][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(smp));
@@ -454,30 +511,6 @@ __global__ void __launch_bounds__(PT_BLOCK) k_bounce(const KParams P)
         if (STATS) P.qout[3][slot] = make_float4(L.x, L.y, L.z, 0.f);
     }
 
-    // ---- counters
-    {
-        const unsigned int pa = n_shadow | (n_miss << 16), pb = n_trunc | ((n_inline + n_shaded) << 16);
-        const unsigned int ra_ = __reduce_add_sync(0xffffffffu, pa), rb_ = __reduce_add_sync(0xffffffffu, pb);
-        const unsigned int rc_ = __reduce_add_sync(0xffffffffu, n_scatter);
-        const unsigned int md = __reduce_max_sync(0xffffffffu, my_depth);
-        if ((threadIdx.x & 31) == 0) {
-            if (ra_ & 0xFFFFu) atomicAdd(&s_stat[0], ra_ & 0xFFFFu);
-            if (ra_ >> 16) atomicAdd(&s_stat[1], ra_ >> 16);
-            if (rb_ & 0xFFFFu) atomicAdd(&s_stat[2], rb_ & 0xFFFFu);
-            if (rb_ >> 16) atomicAdd(&s_stat[3], rb_ >> 16);
-            if (rc_) atomicAdd(&s_stat[4], rc_);
-            atomicMax(&s_stat[5], md);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (s_stat[0]) atomicAdd(&P.stats->rays_shadow, (unsigned long long)s_stat[0]);
-            if (s_stat[1]) atomicAdd(&P.stats->misses, (unsigned long long)s_stat[1]);
-            if (s_stat[2]) atomicAdd(&P.stats->truncated, (unsigned long long)s_stat[2]);
-            if (s_stat[3]) atomicAdd(&P.stats->shaded, (unsigned long long)s_stat[3]);
-            if (s_stat[4]) atomicAdd(&P.stats->rays_scatter, (unsigned long long)s_stat[4]);
-            if (s_stat[5] > 0) atomicMax(&P.stats->max_depth_seen, s_stat[5]);
-        }
-    }
 }
 
 // marks every slot of a queue as dead (depth field = 0xFFFF) so the first bounce regenerates it
@@ -505,12 +538,14 @@ __global__ void k_intersect_fp32(const double *__restrict__ rays, int n_rays, do
     if (i >= n_rays) return;
     const double *r = rays + (size_t)i * 6;
     F3 o = f3((float)r[0], (float)r[1], (float)r[2]), d = f3((float)r[3], (float)r[4], (float)r[5]);
-    float t; int id;
-    closest_hit(o, d, -1, t, id);
-    if (id >= 0) {
-        // report the t the shading stage uses (refined once for the winning object)
-        const MatF32 m = mats[id];
+    float t; int code;
+    closest_hit(o, d, -1, t, code);
+    int id = -1;
+    if (code >= 0) {
+        // report the t the shading stage uses (refined once for the winning object) and the scene id
+        const MatF32 m = mats[code];
         t = refine_t(o, d, t, __float_as_int(m.e_type.w), m.geom, m.aux);
+        id = __float_as_int(m.aux.w);
     }
     t_out[i] = id >= 0 ? (double)t : 1e20;
     id_out[i] = id;
@@ -595,10 +630,14 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         // queue capacity: default keeps both ping-pong queues inside L2 (48 B/path/queue)
         int cap = p->queue_capacity;
         if (cap <= 0) {
+            // whole waves of resident blocks (4 blocks of 256 threads per SM, __launch_bounds__(256, 4)) so that no
+            // launch ends with a partially filled wave, as many as keep both queues within 3/4 of L2
+            const long long wave = (long long)ctx->sm_count * 4 * PT_BLOCK;
             long long budget = (long long)ctx->l2_bytes * 3 / 4;
             if (budget <= 0) budget = 64ll << 20;
-            cap = (int)(budget / (2 * (stats ? 64 : 48)));
-            if (cap < ctx->sm_count * 2048) cap = ctx->sm_count * 2048;
+            long long waves = budget / (2 * (stats ? 64 : 48)) / wave;
+            if (waves < 2) waves = 2;
+            cap = (int)(waves * wave);
         }
         if ((unsigned long long)cap > total) cap = (int)total;
         cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
@@ -632,6 +671,9 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.owned_pixels = (unsigned int)owned_pixels;
         P.inv_owned_pixels = 1.0 / (double)owned_pixels;
         P.w = w; P.h = h; P.spp = p->spp; P.tile_rows = tile; P.rank = p->rank; P.world = world;
+        P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
+        P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
+        P.use_magic = (owned_pixels < (1ull << 24) && w < 65536 && tile < 65536) ? 1 : 0;
         P.max_depth = p->max_depth > 0 ? p->max_depth : 4096;
         if (P.max_depth > 65000) P.max_depth = 65000;
         const pt_camera &c = ctx->cam;
