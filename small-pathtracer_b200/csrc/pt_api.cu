@@ -38,8 +38,14 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
             const DevObj64 &o = ctx->objs[i];
             if (o.type != want) continue;
             if (k < PT_RECT_SLOTS) {
-                S.slot_a[axis][k] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
-                S.slot_b2[axis][k] = (float)o.g[3];
+                // {k, a1, a2 - a1, b1}, b2 - b1: widths as float differences of the float bounds, so that u == a2 (as
+                // floats) still passes:  fl(a2) - fl(a1) rounded up to the next float if needed
+                const float a1 = (float)o.g[0], a2 = (float)o.g[1], b1 = (float)o.g[2], b2 = (float)o.g[3];
+                float wa = a2 - a1, wb = b2 - b1;
+                if (a1 + wa < a2) wa = std::nextafter(wa, INFINITY);
+                if (b1 + wb < b2) wb = std::nextafter(wb, INFINITY);
+                S.slot_a[axis][k] = make_float4((float)o.g[4], a1, wa, b1);
+                S.slot_b2[axis][k] = wb;
                 code_of[i] = axis * PT_RECT_SLOTS + k;
                 k++;
             } else {

@@ -47,8 +47,8 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     float lx0, lxw, lz0, lzw, ly, larea;
     int   n_lights;               // emissive spheres for NEE_CONE_SPHERE
     int   light_sph_code[32];
-    float4 slot_a[3][PT_RECT_SLOTS];   // k, a1, a2, b1   (one 128-bit uniform load)
-    float  slot_b2[3][PT_RECT_SLOTS];  // b2
+    float4 slot_a[3][PT_RECT_SLOTS];   // k, a1, a2 - a1, b1   (one 128-bit uniform load)
+    float  slot_b2[3][PT_RECT_SLOTS];  // b2 - b1
     float4 rect_a[PT_MAX_OBJ];    // overflow rectangles: k, a1, a2, b1
     float  rect_b2[PT_MAX_OBJ];   //                      b2
     float4 sph[PT_MAX_OBJ];       // c.x, c.y, c.z, rad^2
