@@ -149,6 +149,28 @@ def cpu_reference(workload, budget_s, threads=0):
                       f"{res['render_ms'] / 1e3:.1f} s), OpenMP schedule(dynamic,1) over rows, host has {ncores} cores"}, res
 
 
+def secondary(ptb, workload, peak_tf, device_index, stream, flush):
+    """One warm-up + two timed renders of another configuration, device-timed by the library's CUDA events."""
+    scene_name, w, h, spp, mode, desc = WORKLOADS[workload]
+    scene = ptb.builtin_scene(scene_name, w, h)
+    with ptb.Context(scene, device=device_index) as c:
+        p = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0)
+        best = None
+        for i in range(3):
+            flush.fill_(1)
+            stream.synchronize()
+            c.render(p)
+            st = c.stats()
+            if i > 0 and (best is None or st.render_ms < best.render_ms):
+                best = st
+        flops = float(best.rays) * scene.flops_per_ray() + float(best.shaded_vertices) * F_SHADE[mode]
+        tf = flops / (best.render_ms * 1e-3) / 1e12
+        return {"workload": desc, "value": best.paths / best.render_ms * 1e-3, "unit": METRIC, "mrays_per_s": best.rays / best.render_ms * 1e-3,
+                "ms_per_step": best.render_ms, "rays_per_path": best.rays / best.paths, "launches_per_step": int(best.iterations),
+                "roofline": {"bound": "fp32", "kernel": "k_bounce", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                             "flops_per_ray": scene.flops_per_ray(), "flops_per_bounce": F_SHADE[mode]}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,6 +180,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the extra C4 (intersection-bound) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,7 +336,7 @@ def main():
     k_ms = stats.render_ms                                                                   # CUDA events around the launches
     achieved_tf = my_flops / (k_ms * 1e-3) / 1e12
     per_launch_ms = k_ms / max(1, stats.iterations)
-    qbytes = 96.0 * (float(stats.shaded_vertices))                     # 48 B read + 48 B written per path-iteration (upper bound)
+    qbytes = 48.0 * float(stats.queue_slots_io)                       # 48 B per path record read or written through the queues
     roofline = {"bound": "fp32", "kernel": "k_bounce", "achieved": achieved_tf, "peak": ffma_tf or fp32_theory, "unit": "TFLOP/s",
                 "frac": achieved_tf / (ffma_tf or fp32_theory),
                 "peak_source": "FFMA-only microbenchmark measured in this run (pt_debug_ffma_peak)" if ffma_tf else "148 SM x 128 lanes x 2 x sm_max_mhz",
@@ -323,7 +346,7 @@ def main():
                 "traffic": None,
                 "queue": {"bound": "hbm", "achieved": qbytes / (k_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                           "frac": qbytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
-                          "note": "algorithmic queue bytes (96 B per path-iteration); the queues are L2-resident by design"}}
+                          "note": "path records through the wavefront queues x 48 B (a slot advances several bounces per launch in registers)"}}
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -335,6 +358,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback (FP64 image device->host) per step, wall clock"},
             "roofline": roofline}
+    if n_gpus == 1 and not args.no_secondary and workload == "c2":
+        # the intersection-bound configuration (C4) next to the headline: same engine, same accounting
+        try:
+            line["secondary"] = {"c4": secondary(ptb, "c4", ffma_tf or fp32_theory, local_rank, stream, flush)}
+        except Exception as e:                                           # noqa: BLE001
+            line["secondary"] = {"error": str(e)}
     if n_gpus == 1 and not args.no_cpu_baseline:
         try:
             info, _ = cpu_reference(workload, args.cpu_budget)

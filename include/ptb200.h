@@ -127,7 +127,7 @@ typedef struct pt_render_params {
     int      max_depth;       /* safety cap on path length; 0 = default (4096) */
     int      queue_capacity;  /* wavefront queue slots; 0 = default (sized to L2) */
     int      collect_stats;   /* 1 = also accumulate per-pixel sum of squares */
-    int      _pad;
+    int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (8) */
 } pt_render_params;
 
 typedef struct pt_stats {
@@ -144,6 +144,7 @@ typedef struct pt_stats {
     uint32_t _pad;
     double   render_ms;         /* device time of the last pt_render (CUDA events)       */
     double   main_kernel_ms;    /* summed device time of the dominant kernel             */
+    uint64_t queue_slots_io;    /* path records read + written through the wavefront queues */
 } pt_stats;
 
 typedef enum pt_status {

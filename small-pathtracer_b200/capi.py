@@ -58,7 +58,7 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("spp", C.c_int), ("mode", C.c_int),
                 ("engine", C.c_int), ("sincos", C.c_int), ("seed", C.c_uint64),
                 ("tile_rows", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("max_depth", C.c_int),
-                ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("_pad", C.c_int)]
+                ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("bounces_per_launch", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -66,7 +66,7 @@ class Stats(C.Structure):
                 ("rays_shadow", C.c_uint64), ("shaded_vertices", C.c_uint64), ("miss_events", C.c_uint64),
                 ("truncated", C.c_uint64), ("kernel_launches", C.c_uint64), ("iterations", C.c_uint64),
                 ("max_depth_seen", C.c_uint32), ("_pad", C.c_uint32),
-                ("render_ms", C.c_double), ("main_kernel_ms", C.c_double)]
+                ("render_ms", C.c_double), ("main_kernel_ms", C.c_double), ("queue_slots_io", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
@@ -222,11 +222,11 @@ def write_ppm(path, rgb_mean, w, h):
 
 
 def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, sincos=PT_SINCOS_LIBM, seed=0,
-           tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0):
+           tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0, bounces_per_launch=0):
     p = RenderParams()
     p.width, p.height, p.spp, p.mode, p.engine, p.sincos, p.seed = w, h, spp, mode, engine, sincos, seed
     p.tile_rows, p.rank, p.world, p.max_depth = tile_rows, rank, world, max_depth
-    p.queue_capacity, p.collect_stats = queue_capacity, collect_stats
+    p.queue_capacity, p.collect_stats, p.bounces_per_launch = queue_capacity, collect_stats, bounces_per_launch
     return p
 
 

@@ -92,6 +92,29 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
             code_of[i] = S.code_tilt0 + S.n_tilt++;
         }
     }
+    {   // conservative scan form of the small spheres: translate so the cloud of centres is centred on the origin
+        // (smaller magnitudes => smaller FP32 cancellation error in b = c'.d - o'.d and c = |c'|^2 - r^2 - 2 c'.o' + |o'|^2)
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = 0; i < n; i++) {
+            const DevObj64 &o = ctx->objs[i];
+            if (o.type != OT_SPHERE || o.g[0] >= PT_HUGE_RADIUS) continue;
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], o.g[1 + a]); hi[a] = std::fmax(hi[a], o.g[1 + a]); }
+        }
+        for (int a = 0; a < 3; a++) S.sph_c[a] = S.n_sph ? (float)(0.5 * (lo[a] + hi[a])) : 0.f;
+        double M2 = 0;
+        for (int k = 0; k < S.n_sph; k++) {
+            const float4 c = S.sph[k];               // the FP32 centre the exact test uses
+            const float x = (float)((double)c.x - (double)S.sph_c[0]), y = (float)((double)c.y - (double)S.sph_c[1]),
+                        z = (float)((double)c.z - (double)S.sph_c[2]);
+            const double n2 = (double)x * x + (double)y * y + (double)z * z;
+            S.sphf[k] = make_float4(x, y, z, (float)(n2 - (double)c.w));
+            const double m = std::sqrt(n2) + std::sqrt((double)c.w);
+            M2 = std::fmax(M2, m * m);
+        }
+        S.n_sph4 = (S.n_sph + 3) / 4 * 4;
+        for (int k = S.n_sph; k < S.n_sph4; k++) S.sphf[k] = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+        S.sph_kM2 = (float)(PT_SPH_KAPPA * M2);
+    }
     S.code_obj0 = code_of[0];
     S.light_code = (ctx->light.id >= 0 && ctx->light.id < n) ? code_of[ctx->light.id] : -2;
     S.lx0 = (float)ctx->light.x0; S.lxw = (float)ctx->light.xw;
@@ -175,11 +198,19 @@ static int upload_tables(pt_ctx *ctx)
         const int nc = (int)mats.size();
         if (ctx->n_codes_alloc < nc) {
             if (ctx->d_mats) cudaFree(ctx->d_mats);
+    if (ctx->d_sphf) cudaFree(ctx->d_sphf);
             ctx->d_mats = nullptr; ctx->n_codes_alloc = 0;
             PT_CUDA(ctx, cudaMalloc(&ctx->d_mats, sizeof(MatF32) * nc));
             ctx->n_codes_alloc = nc;
         }
         PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), sizeof(MatF32) * nc, cudaMemcpyHostToDevice, ctx->stream));
+        // global-memory mirror of the sphere scan table: k_bounce stages it in shared memory
+        if (!ctx->d_sphf) PT_CUDA(ctx, cudaMalloc(&ctx->d_sphf, 2 * sizeof(float4) * (PT_MAX_OBJ + 4)));
+        if (ctx->h_scene32->n_sph4 > 0) {
+            // scan table, then (at PT_MAX_OBJ + 4) the exact {centre, r^2} table; padding entries are never candidates
+            PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sphf, ctx->h_scene32->sphf, sizeof(float4) * ctx->h_scene32->n_sph4, cudaMemcpyHostToDevice, ctx->stream));
+            PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sphf + PT_MAX_OBJ + 4, ctx->h_scene32->sph, sizeof(float4) * ctx->h_scene32->n_sph, cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PT_OK;
@@ -426,6 +457,7 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 4; b++) if (ctx->q[a][b]) cudaFree(ctx->q[a][b]);
+    if (ctx->d_warp_chunk) cudaFree(ctx->d_warp_chunk);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->d_fix) cudaFree(ctx->d_fix);
     if (ctx->d_fixsq) cudaFree(ctx->d_fixsq);
@@ -433,6 +465,7 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
     if (ctx->d_objs) cudaFree(ctx->d_objs);
     if (ctx->d_mats) cudaFree(ctx->d_mats);
+    if (ctx->d_sphf) cudaFree(ctx->d_sphf);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);

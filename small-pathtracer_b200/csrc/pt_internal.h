@@ -28,6 +28,8 @@ struct DevObj64 {
 #define PT_MAX_TILT       64
 #define PT_HUGE_RADIUS    100.0   // spheres at least this big take the FP64 c-term path
 
+#define PT_SPH_KAPPA      3.814697265625e-6f   /* 2^-18: relative slack of the conservative sphere scan */
+
 #define PT_RECT_SLOTS     16      // rectangles per axis class tested by fully unrolled, constant-operand code
 
 // The FP32 engine addresses objects by CODE (position in the class-sorted layout), not by scene id:
@@ -52,6 +54,12 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     float4 rect_a[PT_MAX_OBJ];    // overflow rectangles: k, a1, a2, b1
     float  rect_b2[PT_MAX_OBJ];   //                      b2
     float4 sph[PT_MAX_OBJ];       // c.x, c.y, c.z, rad^2
+    // conservative scan form of the same spheres (see closest_hit): centres relative to sph_c, w = |c'|^2 - rad^2;
+    // padded to a multiple of 4 with entries that can never pass (w = 3e38)
+    float4 sphf[PT_MAX_OBJ + 4];
+    float  sph_c[3];              // translation that centres the small spheres around the origin
+    float  sph_kM2;               // PT_SPH_KAPPA * max_i (|c'_i| + rad_i)^2
+    int    n_sph4;                // n_sph rounded up to a multiple of 4
     double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64
     float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
 };
@@ -82,6 +90,7 @@ struct pt_ctx {
     int n_alloc = 0;                   // objects d_objs / d_mats can hold
     SceneF32 *h_scene32 = nullptr;     // host staging copy (heap; copied to __constant__ before FP32 launches)
     MatF32 *d_mats = nullptr;          // indexed by code
+    float4 *d_sphf = nullptr;          // SceneF32::sphf mirrored in global memory (staged into shared memory by k_bounce)
     int n_codes_alloc = 0;
     bool fp32_ok = false;              // scene fits the FP32 constant layout
     std::string fp32_why;
@@ -96,6 +105,7 @@ struct pt_ctx {
     // wavefront queues (FP32 engine)
     float4 *q[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     int q_capacity = 0;
+    uint4 *d_warp_chunk = nullptr;                     // per warp: path indices reserved but not yet traced
     unsigned int *d_counts = nullptr;                  // per-iteration live counts etc.
     int counts_len = 0;
     size_t counts_dirty = 0;

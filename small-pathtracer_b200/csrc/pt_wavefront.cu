@@ -42,15 +42,31 @@ namespace {
 #define PT_BLOCK 256
 #endif
 #ifndef PT_BLOCKS_PER_SM
-#define PT_BLOCKS_PER_SM (1280 / PT_BLOCK)   /* 5 blocks of 256: 48 registers/thread, measured 3 % faster than 4 */
+#define PT_BLOCKS_PER_SM (1024 / PT_BLOCK)   /* 4 blocks of 256: 64 registers/thread keep the bounce loop's state out of local memory */
+#endif
+#ifndef PT_DEFAULT_WAVES
+#define PT_DEFAULT_WAVES 4
+#endif
+#ifndef PT_DEFAULT_ITERS
+#define PT_DEFAULT_ITERS 16         /* bounces per launch while camera paths are being generated */
+#endif
+#ifndef PT_DEFAULT_ITERS_TAIL
+#define PT_DEFAULT_ITERS_TAIL 2     /* ... once generation is exhausted (compaction pays in the tail) ... */
+#endif
+#ifndef PT_DEFAULT_ITERS_DRAIN
+#define PT_DEFAULT_ITERS_DRAIN 16   /* ... and once the survivors no longer fill the GPU (launch latency dominates) */
 #endif
 
 struct KParams {
     float4 *qin[4];
     float4 *qout[4];
-    const unsigned int *n_in;          // live count of the input queue (this iteration)
-    unsigned int *n_out;               // survivors (next iteration), zero before the launch
-    unsigned long long *gen_counter;   // next path index to generate
+    const unsigned int *n_in;          // live count of the input queue (this launch)
+    unsigned int *n_out;               // survivors (next launch), zero before the launch
+    unsigned long long *gen_counter;   // next path index to hand out (advanced PT chunk by chunk, one atomic per warp)
+    uint4 *warp_chunk;                 // per warp: {base lo, base hi, left, -} of the path indices it still holds
+    int iters, iters_tail, iters_drain; // bounces per launch: generating / generation exhausted / survivors < drain_below
+    unsigned int drain_below;
+    unsigned int chunk;                // path indices a warp reserves per atomic (>= 32)
     unsigned long long total_paths;
     unsigned int owned_pixels;
     double inv_owned_pixels;
@@ -63,6 +79,7 @@ struct KParams {
     unsigned long long *fix;           // w*h*3 fixed-point sums
     unsigned long long *fixsq;         // w*h*3 fixed-point sums of squares (STATS only)
     const MatF32 *mats;
+    const float4 *sphf;                // SceneF32::sphf in global memory
     DevStats *stats;
 };
 
@@ -74,10 +91,11 @@ __device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y -
 __device__ __forceinline__ F3 operator*(F3 a, float b) { return f3(a.x * b, a.y * b, a.z * b); }
 __device__ __forceinline__ F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ F3 fma3(F3 d, float t, F3 o) { return f3(fmaf(d.x, t, o.x), fmaf(d.y, t, o.y), fmaf(d.z, t, o.z)); }
-__device__ __forceinline__ F3 normalize3(F3 a) { return a * rsqrtf(dot3(a, a)); }
-
-__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// single-MUFU approximations (the .ftz forms: without it every call drags a denormal-rescaling sequence along)
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ F3 normalize3(F3 a) { return a * rsqrt_fast(dot3(a, a)); }
 
 // ---------------------------------------------------------------------------------------------- extend
 // One rectangle of the reference (:102-112 / :145-155 / :188-198): t = (k - o_a) / d_a, the two in-plane
@@ -137,7 +155,7 @@ __device__ __forceinline__ void rects_axis(float oa, float ia, float ou, float d
 #else
 #define PT_HIT_INLINE __forceinline__
 #endif
-__device__ PT_HIT_INLINE void closest_hit(F3 o, F3 d, int prev, float &t_out, int &code_out)
+__device__ PT_HIT_INLINE void closest_hit(F3 o, F3 d, int prev, const float4 *__restrict__ s_sphf, float &t_out, int &code_out)
 {
     float best = 1e20f;
     int code = -1;
@@ -146,23 +164,60 @@ __device__ PT_HIT_INLINE void closest_hit(F3 o, F3 d, int prev, float &t_out, in
     rects_axis<1>(o.z, iz, o.x, d.x, o.y, d.y, best, code);   // XY: plane z
     rects_axis<2>(o.x, ix, o.y, d.y, o.z, d.z, best, code);   // YZ: plane x
 
-    // Sphere::intersect, :229-239, eps = 1e-4.  det = r^2 - |op - b d|^2 (perpendicular distance form).
-    const int ns = c_scene.n_sph;
-    const int prev_s = prev - c_scene.code_sph0;
-#pragma unroll 4
-    for (int i = 0; i < ns; i++) {
-        const float4 s = c_scene.sph[i];
-        F3 op = f3(s.x - o.x, s.y - o.y, s.z - o.z);
-        float b = dot3(op, d);
-        F3 l = f3(fmaf(-b, d.x, op.x), fmaf(-b, d.y, op.y), fmaf(-b, d.z, op.z));
-        float det = s.w - dot3(l, l);
-        if (det >= 0.f) {
-            float sq = sqrt_fast(det);
-            float t0 = b - sq, t1 = b + sq;
-            float tt = t0 > PT_EPS_F ? t0 : t1;
-            if (i == prev_s) tt = b + b;          // origin on this sphere: roots are exactly {0, 2b}
-            if (tt > PT_EPS_F && tt < best) { best = tt; code = c_scene.code_sph0 + i; }
+    // Sphere::intersect, :229-239, eps = 1e-4, in two stages.
+    // Scan (every sphere; LDS.128 + 7 FFMA + compare + mask bit): with centres c' and the origin o' relative to sph_c,
+    //   b = c'.d - o'.d,   det - |o'|^2 = b^2 - (|c'|^2 - r^2 - 2 c'.o')
+    // needs no per-sphere subtraction; its FP32 cancellation error is bounded by a few ulp of (|c'| + |o'|)^2, so the
+    // test `det >= -kappa ((max|c'| + r)^2 + |o'|^2)` is CONSERVATIVE (kappa = 2^-18, ~5x the bound): it never rejects
+    // a sphere the exact test would accept.  Candidates of 32 spheres are collected in a per-lane bit mask, branch-free.
+    // Exact stage (rare): every lane pops ITS candidates (lowest index first; lanes work on different spheres at the
+    // same time, so the warp runs max-over-lanes iterations, typically 1-2 per 32 spheres): the perpendicular-distance
+    // discriminant det = r^2 - |op - b d|^2 on the un-translated data.
+    const int ns4 = c_scene.n_sph4;
+    if (ns4 > 0) {
+        const F3 oc = f3(o.x - c_scene.sph_c[0], o.y - c_scene.sph_c[1], o.z - c_scene.sph_c[2]);
+        const float O2 = dot3(oc, oc), OD = dot3(oc, d);
+        const float thr = fmaf(O2, 1.f - PT_SPH_KAPPA, -c_scene.sph_kM2);
+        const F3 o2 = oc * -2.f;
+        const int prev_s = prev - c_scene.code_sph0;
+        const float4 *s_sphx = s_sphf + (PT_MAX_OBJ + 4);     // exact data {centre, r^2} behind the scan table
+#define PT_SPH_SCAN(IDX, BIT)                                                                               \
+        {                                                                                                   \
+            const float4 s = s_sphf[IDX];                                                                   \
+            const float b = fmaf(s.x, d.x, fmaf(s.y, d.y, fmaf(s.z, d.z, -OD)));                            \
+            const float c = fmaf(s.x, o2.x, fmaf(s.y, o2.y, fmaf(s.z, o2.z, s.w)));                         \
+            if (fmaf(b, b, -c) >= thr) mask |= (BIT);                                                       \
         }
+#pragma unroll 1
+        for (int base = 0; base < ns4; base += 32) {
+            unsigned int mask = 0u;
+            if (base + 32 <= ns4) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) PT_SPH_SCAN(base + k, 1u << k)
+            } else {
+#pragma unroll 1
+                for (int g = 0; base + g < ns4; g += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) PT_SPH_SCAN(base + g + k, (1u << k) << g)
+                }
+            }
+            while (mask) {
+                const int i = base + __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const float4 s = s_sphx[i];
+                F3 op = f3(s.x - o.x, s.y - o.y, s.z - o.z);
+                float b = dot3(op, d);
+                F3 l = f3(fmaf(-b, d.x, op.x), fmaf(-b, d.y, op.y), fmaf(-b, d.z, op.z));
+                float dd = s.w - dot3(l, l);
+                float sq = sqrt_fast(fmaxf(dd, 0.f));
+                float t0 = b - sq, t1 = b + sq;
+                float tt = t0 > PT_EPS_F ? t0 : t1;
+                if (i == prev_s) tt = b + b;          // origin on this sphere: roots are exactly {0, 2b}
+                // ascending i with strict < keeps the lowest id on ties (:328)
+                if (dd >= 0.f && tt > PT_EPS_F && tt < best) { best = tt; code = c_scene.code_sph0 + i; }
+            }
+        }
+#undef PT_SPH_SCAN
     }
     // Huge spheres (the 1e5-radius walls of the sphere-era scene): c in FP64, conjugate roots in FP32.
     const int nh = c_scene.n_huge;
@@ -208,30 +263,28 @@ __device__ PT_HIT_INLINE void closest_hit(F3 o, F3 d, int prev, float &t_out, in
 // ~1e-7 relative accuracy even where FP32 cannot represent k (81.6, 81.5).
 // Small spheres: one Newton step on |o + d t - c|^2 = r^2 from the hit point (numbers near the surface are
 // small, so the residual is accurate where the quadratic's coefficients were not).
-__device__ __forceinline__ float refine_t(F3 o, F3 d, float t, int type, float4 geom, float4 aux)
+__device__ __forceinline__ void refine_hit(F3 o, F3 d, float &t, int type, float4 geom, float4 aux, F3 &x)
 {
-    if (type == OT_XZ) return __fdiv_rn((geom.x - o.y) + geom.y, d.y);
-    if (type == OT_XY) return __fdiv_rn((geom.x - o.z) + geom.y, d.z);
-    if (type == OT_YZ) return __fdiv_rn((geom.x - o.x) + geom.y, d.x);
+    if (type >= OT_XZ && type <= OT_YZ) {
+        // one IEEE division for the three axis classes: pick the plane's axis component first
+        const float oa = type == OT_XZ ? o.y : type == OT_XY ? o.z : o.x;
+        const float da = type == OT_XZ ? d.y : type == OT_XY ? d.z : d.x;
+        t = __fdiv_rn((geom.x - oa) + geom.y, da);
+        const float xa = __fadd_rn(oa, __fmul_rn(da, t));     // the reference's o + d*t, no FMA (:375)
+        x = fma3(d, t, o);
+        if (type == OT_XZ) x.y = xa; else if (type == OT_XY) x.z = xa; else x.x = xa;
+        return;
+    }
     if (type == OT_TILT)       // n.(p0 - o) / n.d with the difference taken first and IEEE division
-        return __fdiv_rn(dot3(f3(geom.x, geom.y, geom.z), f3(aux.x - o.x, aux.y - o.y, aux.z - o.z)), dot3(f3(geom.x, geom.y, geom.z), d));
-    if (type == OT_SPHERE && geom.w > (1.f / (float)PT_HUGE_RADIUS)) {
+        t = __fdiv_rn(dot3(f3(geom.x, geom.y, geom.z), f3(aux.x - o.x, aux.y - o.y, aux.z - o.z)), dot3(f3(geom.x, geom.y, geom.z), d));
+    else if (geom.w > (1.f / (float)PT_HUGE_RADIUS)) {        // small sphere
         const float rad = 1.f / geom.w;
         F3 r = f3(fmaf(d.x, t, o.x) - geom.x, fmaf(d.y, t, o.y) - geom.y, fmaf(d.z, t, o.z) - geom.z);
         const float f = fmaf(r.x, r.x, fmaf(r.y, r.y, fmaf(r.z, r.z, -rad * rad)));
         const float g = 2.f * dot3(r, d);
         if (fabsf(g) > 1e-3f * rad) t -= f / g;
     }
-    return t;
-}
-
-__device__ __forceinline__ F3 hit_point(F3 o, F3 d, float t, int type)
-{
-    F3 x = fma3(d, t, o);
-    if (type == OT_XZ) x.y = __fadd_rn(o.y, __fmul_rn(d.y, t));
-    else if (type == OT_XY) x.z = __fadd_rn(o.z, __fmul_rn(d.z, t));
-    else if (type == OT_YZ) x.x = __fadd_rn(o.x, __fmul_rn(d.x, t));
-    return x;
+    x = fma3(d, t, o);
 }
 
 // random_scattering: cosine-weighted (:337-348) or uniform (:351-360; weight 1 as in the reference)
@@ -265,53 +318,134 @@ __device__ __forceinline__ unsigned int pack_state(int depth, int prev, int E)
 }
 
 // ---------------------------------------------------------------------------------------------- the bounce kernel
+// One launch = up to P.iters bounces of every path slot, state in registers:
+//   load (queue) -> [ regenerate dead lanes -> bounce ] x iters -> compact survivors (queue).
+// A lane whose path ended takes the next camera path at once, so lanes stay busy without a trip through the
+// queue; the queue and the block-wide compaction run once per launch and matter in the tail of a render, when
+// generation is exhausted and the survivors of long paths are repacked into dense warps.
+// Path indices are handed out in chunks: a warp reserves P.chunk consecutive indices with ONE atomic and keeps
+// what it has not used in P.warp_chunk between launches, so regeneration needs no block-wide step.
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KParams P)
 {
-    __shared__ unsigned int s_alive[PT_BLOCK / 32], s_want[PT_BLOCK / 32];
-    __shared__ unsigned int s_base_out, s_regen_ok;
-    __shared__ unsigned long long s_base_gen;
-    __shared__ unsigned int s_stat[6];   // shadow, miss, truncated, shaded (+inline), scatter, max depth
+    constexpr unsigned int NW = PT_BLOCK / 32;
+    __shared__ unsigned int s_warp[NW][8];   // per warp: alive, shadow, miss | trunc << 16, shaded, scatter, max depth
+    __shared__ unsigned int s_base_out;
+    __shared__ float4 s_sphf[2 * (PT_MAX_OBJ + 4)];    // sphere scan table, then the exact {centre, r^2} table
 
     const unsigned int tid = blockIdx.x * PT_BLOCK + threadIdx.x;
+    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    // every load of the prologue is independent of the others: one L2 round trip, not three
     const unsigned int n_in = *P.n_in;
-    if (blockIdx.x * PT_BLOCK >= n_in) return;          // whole block beyond the queue
-    if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
-    __syncthreads();
-    const bool have = tid < n_in;
+    const unsigned long long gen_seen = *(volatile unsigned long long *)P.gen_counter;
+    const uint4 wc = P.warp_chunk[tid >> 5];
+    const float4 qa = P.qin[0][tid], qb = P.qin[1][tid], qc = P.qin[2][tid];
+    float4 ql = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STATS) ql = P.qin[3][tid];
+    // stage the sphere scan table (16 B per sphere) in shared memory
+    if (c_scene.n_sph4 > 0) {
+#pragma unroll 1
+        for (int i = threadIdx.x; i < c_scene.n_sph4; i += PT_BLOCK) {
+            s_sphf[i] = P.sphf[i];
+            s_sphf[PT_MAX_OBJ + 4 + i] = P.sphf[PT_MAX_OBJ + 4 + i];
+        }
+        __syncthreads();
+    }
 
     F3 o = f3(0, 0, 0), d = f3(0, 0, 1), T = f3(0, 0, 0), L = f3(0, 0, 0);
     unsigned int pix = 0, smp = 0;
     int depth = 0, prev = -1, E = 1;
     bool alive = false;
-    unsigned int n_shadow = 0, n_miss = 0, n_trunc = 0, n_inline = 0, n_shaded = 0, my_depth = 0;
+    unsigned int n_shadow = 0, n_miss = 0, n_trunc = 0, n_shaded = 0, n_scatter = 0, my_depth = 0;
+    if (tid < n_in) {
+        const unsigned int st = __float_as_uint(qc.w);
+        o = f3(qa.x, qa.y, qa.z); pix = __float_as_uint(qa.w);
+        d = f3(qb.x, qb.y, qb.z); smp = __float_as_uint(qb.w);
+        T = f3(qc.x, qc.y, qc.z);
+        depth = (int)(st & 0xFFFFu); prev = (int)((st >> 16) & 0x7FFFu) - 1; E = (int)(st >> 31);
+        if (STATS) L = f3(ql.x, ql.y, ql.z);
+        alive = true;
+    }
+    unsigned long long ck_base = (unsigned long long)wc.x | ((unsigned long long)wc.y << 32);
+    unsigned int ck_left = wc.z;
+    bool exhausted = gen_seen >= P.total_paths;          // monotonic counter: a stale read only delays the switch
+    const int iters = !exhausted ? P.iters : (n_in < P.drain_below ? P.iters_drain : P.iters_tail);
 
-    if (have) {
-        const float4 c = P.qin[2][tid];
-        const unsigned int st = __float_as_uint(c.w);
-        if ((st & 0xFFFFu) != PT_DEPTH_DEAD) {
-            const float4 a = P.qin[0][tid], b = P.qin[1][tid];
-            o = f3(a.x, a.y, a.z); pix = __float_as_uint(a.w);
-            d = f3(b.x, b.y, b.z); smp = __float_as_uint(b.w);
-            T = f3(c.x, c.y, c.z);
-            depth = (int)(st & 0xFFFFu); prev = (int)((st >> 16) & 0x7FFFu) - 1; E = (int)(st >> 31);
-            if (STATS) { const float4 l4 = P.qin[3][tid]; L = f3(l4.x, l4.y, l4.z); }
+    for (int it = 0;; it++) {
+    // ---- regeneration: lanes without a path take the warp's next path indices (:528-536)
+    const unsigned int b_want = __ballot_sync(0xffffffffu, !alive);
+    if (b_want != 0u && (ck_left > 0u || !exhausted)) {            // warp-uniform
+        const unsigned int n = __popc(b_want), r = __popc(b_want & lt);
+        unsigned long long g = 0;
+        bool got = false;
+        if (ck_left < n && !exhausted) {
+            // refill: the rest of the old chunk goes to the first lanes, the new chunk to the others
+            unsigned long long g0 = 0;
+            if (lane == 0) g0 = atomicAdd(P.gen_counter, (unsigned long long)P.chunk);
+            g0 = __shfl_sync(0xffffffffu, g0, 0);
+            const unsigned int fresh = g0 >= P.total_paths ? 0u : (unsigned int)min((unsigned long long)P.chunk, P.total_paths - g0);
+            if (fresh < P.chunk) exhausted = true;
+            if (r < ck_left) { g = ck_base + r; got = true; }
+            else if (r - ck_left < fresh) { g = g0 + (r - ck_left); got = true; }
+            const unsigned int used = min(n - ck_left, fresh);
+            ck_base = g0 + used; ck_left = fresh - used;
+        } else {
+            if (r < ck_left) { g = ck_base + r; got = true; }
+            const unsigned int used = min(n, ck_left);
+            ck_base += used; ck_left -= used;
+        }
+        if (!alive && got) {
+            // path g -> (sample, owned pixel): pixel-major inside a sample so neighbouring lanes are neighbouring pixels
+            unsigned int sidx = (unsigned int)__double2uint_rz(__ull2double_rz(g) * P.inv_owned_pixels);
+            long long rr = (long long)(g - (unsigned long long)sidx * P.owned_pixels);
+            if (rr < 0) { sidx--; rr += P.owned_pixels; }
+            else if (rr >= (long long)P.owned_pixels) { sidx++; rr -= P.owned_pixels; }
+            const unsigned int lp = (unsigned int)rr;
+            unsigned int row_local, tile;
+            if (P.use_magic) {               // multiply-shift division (warp-uniform branch)
+                row_local = (unsigned int)(((unsigned long long)lp * P.magic_w) >> 40);
+                tile = (unsigned int)(((unsigned long long)row_local * P.magic_tile) >> 40);
+            } else {
+                row_local = lp / (unsigned int)P.w;
+                tile = row_local / (unsigned int)P.tile_rows;
+            }
+            const unsigned int xpix = lp - row_local * (unsigned int)P.w;
+            const unsigned int y = (tile * (unsigned int)P.world + (unsigned int)P.rank) * (unsigned int)P.tile_rows
+                                 + (row_local - tile * (unsigned int)P.tile_rows);
+            pix = y * (unsigned int)P.w + xpix;
+            smp = sidx;
+            // ray generation with uniform sub-pixel jitter (:533-536)
+            const uint4 rj = philox4x32_10(pix, smp, 0u, PT_DRAW_A, P.seed_lo, P.seed_hi);
+            const float u = ((float)xpix - 0.5f + u01(rj.x)) * P.inv_w;                            // :533
+            const float v = ((float)(P.h - 1 - (int)y) - 0.5f + u01(rj.y)) * P.inv_h;              // :534
+            F3 dc = f3(fmaf(P.cam_h[0], u, fmaf(P.cam_v[0], v, P.cam_base[0])),
+                       fmaf(P.cam_h[1], u, fmaf(P.cam_v[1], v, P.cam_base[1])),
+                       fmaf(P.cam_h[2], u, fmaf(P.cam_v[2], v, P.cam_base[2])));                    // :276-279
+            d = normalize3(dc);                                                                    // :536
+            o = f3(P.cam_o[0], P.cam_o[1], P.cam_o[2]);
+            T = f3(1.f, 1.f, 1.f);
+            L = f3(0.f, 0.f, 0.f);
+            depth = 0; prev = -1; E = 1;
             alive = true;
         }
     }
+    if (it >= iters) break;
+    if (!__any_sync(0xffffffffu, alive)) break;                     // nothing left to trace in this warp
 
     if (alive) {
         // ---- extend: closest hit (:323-335) + hittingPoint (:371-377)
         float t; int code;
-        n_shaded = 1;
-        closest_hit(o, d, prev, t, code);
+        F3 Lc;                      // radiance this vertex contributes (emission, light samples): ONE accumulation per bounce
+        n_shaded++;
+        closest_hit(o, d, prev, s_sphf, t, code);
         F3 x;
         int on_code;
         if (code < 0) { x = f3(0.f, 0.f, 0.f); code = c_scene.code_obj0; on_code = -1; n_miss++; }   // :373-374: continue from (0,0,0) on object 0
         else on_code = code;
         const MatF32 m = P.mats[code];
         const int type = __float_as_int(m.e_type.w), refl = __float_as_int(m.c_refl.w);
-        if (on_code >= 0) { t = refine_t(o, d, t, type, m.geom, m.aux); x = hit_point(o, d, t, type); }
+        if (on_code >= 0) refine_hit(o, d, t, type, m.geom, m.aux, x);
         // ---- normal(), :118-124 / :246-253
         F3 ng;
         if (type == OT_SPHERE) ng = f3(x.x - m.geom.x, x.y - m.geom.y, x.z - m.geom.z) * m.geom.w;
@@ -323,15 +457,13 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KPa
         F3 f = f3(m.c_refl.x, m.c_refl.y, m.c_refl.z);
         F3 e = f3(m.e_type.x, m.e_type.y, m.e_type.z);
         if (MODE == PT_MODE_NEE_CONE_SPHERE && !E && type == OT_SPHERE) e = f3(0.f, 0.f, 0.f);
-        if (e.x > 0.f || e.y > 0.f || e.z > 0.f) {
-            if (STATS) L = L + T * e; else accum_add(P.fix, pix, T * e);
-        }
+        Lc = T * e;
         // ---- Russian roulette, :447-454.  One Philox block per vertex: x -> RR (high 16 bits) and the REFR
         // branch (low 16 bits); y, z -> the two sampling uniforms of the first decision (light point or
         // hemisphere); w and the unused low bytes of y, z, w -> the hemisphere sample after an occluded light.
         const float p = f.x > f.y && f.x > f.z ? f.x : f.y > f.z ? f.y : f.z;
         depth++;
-        my_depth = depth;
+        my_depth = max(my_depth, (unsigned int)depth);
         const uint4 ra = philox4x32_10(pix, smp, (unsigned)depth, PT_DRAW_A, P.seed_lo, P.seed_hi);
         if (depth > 5 || p == 0.f) {
             if ((float)(ra.x >> 16) * (1.f / 65536.f) < p) f = f * (1.f / p);
@@ -347,7 +479,7 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KPa
                     F3 dl = normalize3(f3(xl - x.x, c_scene.ly - x.y, zl - x.z));
                     float ts; int cs;
                     n_shadow++;
-                    closest_hit(x, dl, on_code, ts, cs);
+                    closest_hit(x, dl, on_code, s_sphf, ts, cs);
                     if (cs == c_scene.light_code) {
                         const float pdf_inv = fabsf(c_scene.larea * dl.y / (ts * ts));   // :471
                         const float brdf = fabsf(dot3(dl, nl) * PT_INV_PI_F);            // :472
@@ -358,9 +490,9 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KPa
                             // the path continues along the shadow ray and ends on the (black-bodied) light:
                             // !p => one RR draw, xi < 0 is false => return e (:448-453).  Finished in place.
                             const F3 el = f3(ml.e_type.x, ml.e_type.y, ml.e_type.z);
-                            if (STATS) L = L + T * el; else accum_add(P.fix, pix, T * el);
-                            n_inline++;
-                            my_depth = depth + 1;
+                            Lc = Lc + T * el;
+                            n_shaded++;
+                            my_depth = max(my_depth, (unsigned int)depth + 1u);
                             alive = false;
                         } else {
                             dn = dl;       // general light with albedo: keep tracing from here next bounce
@@ -393,16 +525,14 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KPa
                         F3 l = normalize3(su * (cp * sin_a) + sv * (sp * sin_a) + sw * cos_a);
                         float ts; int cs;
                         n_shadow++;
-                        closest_hit(x, l, on_code, ts, cs);
+                        closest_hit(x, l, on_code, s_sphf, ts, cs);
                         if (cs == lc) {
                             const float omega = 2.f * PT_PI_F * (1.f - cos_a_max);
                             const float ldn = dot3(l, nl);
                             if (ldn > 0.f) esum = esum + f * f3(ml.e_type.x, ml.e_type.y, ml.e_type.z) * (ldn * omega * PT_INV_PI_F);
                         }
                     }
-                    if (esum.x > 0.f || esum.y > 0.f || esum.z > 0.f) {
-                        if (STATS) L = L + T * esum; else accum_add(P.fix, pix, T * esum);
-                    }
+                    Lc = Lc + T * esum;
                     T = T * f;
                     E = 0;
                 } else {
@@ -432,116 +562,58 @@ __global__ void __launch_bounds__(PT_BLOCK, PT_BLOCKS_PER_SM) k_bounce(const KPa
                     else { dn = td; T = T * (Tr / (1.f - Pr)); }
                 }
             }
-            if (alive) { o = x; d = dn; prev = on_code; }
+            if (alive) { o = x; d = dn; prev = on_code; n_scatter++; }
         }
-        if (!alive && STATS) {
-            // path finished: flush its radiance and its square
-            accum_add(P.fix, pix, L);
-            accum_add(P.fixsq, pix, L * L);
-        }
+        if (STATS) {
+            L = L + Lc;
+            if (!alive) {       // path finished: flush its radiance and its square
+                accum_add(P.fix, pix, L);
+                accum_add(P.fixsq, pix, L * L);
+            }
+        } else if (Lc.x > 0.f || Lc.y > 0.f || Lc.z > 0.f) accum_add(P.fix, pix, Lc);
     }
 
-    // ---- regeneration + compaction in ONE block-wide phase.
-    // Survivors are ranked by warp ballot + block prefix sum; lanes whose path ended ("want") are ranked the same
-    // way and get consecutive new path indices from ONE 64-bit atomic per block; the block's output slots come from
-    // ONE 32-bit atomic per block: survivors first, regenerated paths behind them.
-    const bool want = have && !alive;
-    const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int b_alive = __ballot_sync(0xffffffffu, alive), b_want = __ballot_sync(0xffffffffu, want);
-    {   // counters: two warp reductions + a max, folded into the same barrier phase (scatter rays = survivors)
-        const unsigned int pa = n_shadow | (n_miss << 16), pb = n_trunc | ((n_inline + n_shaded) << 16);
-        const unsigned int ra_ = __reduce_add_sync(0xffffffffu, pa), rb_ = __reduce_add_sync(0xffffffffu, pb);
+    }   // bounce loop
+
+    // ---- compaction of the survivors into the output queue: warp ballot + block prefix sum + ONE atomic per block
+    const unsigned int b_alive = __ballot_sync(0xffffffffu, alive);
+    {
+        const unsigned int r0 = __reduce_add_sync(0xffffffffu, n_shadow), r1 = __reduce_add_sync(0xffffffffu, n_miss | (n_trunc << 16));
+        const unsigned int r2 = __reduce_add_sync(0xffffffffu, n_shaded), r3 = __reduce_add_sync(0xffffffffu, n_scatter);
         const unsigned int md = __reduce_max_sync(0xffffffffu, my_depth);
         if (lane == 0) {
-            s_alive[warp] = __popc(b_alive); s_want[warp] = __popc(b_want);
-            if (ra_ & 0xFFFFu) atomicAdd(&s_stat[0], ra_ & 0xFFFFu);
-            if (ra_ >> 16) atomicAdd(&s_stat[1], ra_ >> 16);
-            if (rb_ & 0xFFFFu) atomicAdd(&s_stat[2], rb_ & 0xFFFFu);
-            if (rb_ >> 16) atomicAdd(&s_stat[3], rb_ >> 16);
-            atomicMax(&s_stat[5], md);
+            s_warp[warp][0] = __popc(b_alive); s_warp[warp][1] = r0; s_warp[warp][2] = r1; s_warp[warp][3] = r2;
+            s_warp[warp][4] = r3; s_warp[warp][5] = md;
+            P.warp_chunk[tid >> 5] = make_uint4((unsigned int)ck_base, (unsigned int)(ck_base >> 32), ck_left, 0u);
         }
     }
     __syncthreads();
-    unsigned int alive_before = 0, alive_total = 0, want_before = 0, want_total = 0;
-#pragma unroll
-    for (int i = 0; i < PT_BLOCK / 32; i++) {
-        const unsigned int ca = s_alive[i], cw = s_want[i];
-        alive_before += (i < (int)warp) ? ca : 0u; alive_total += ca;
-        want_before += (i < (int)warp) ? cw : 0u; want_total += cw;
-    }
-    if (threadIdx.x == 0) {
-        unsigned long long g0 = 0;
-        unsigned int ok = 0;
-        if (want_total) {
-            g0 = atomicAdd(P.gen_counter, (unsigned long long)want_total);
-            ok = g0 >= P.total_paths ? 0u : (unsigned int)min((unsigned long long)want_total, P.total_paths - g0);
+    const unsigned int cnt = lane < NW ? s_warp[lane][0] : 0u;
+    const unsigned int alive_total = __reduce_add_sync(0xffffffffu, cnt), alive_before = __reduce_add_sync(0xffffffffu, lane < warp ? cnt : 0u);
+    if (warp == 0) {
+        const unsigned int v1 = lane < NW ? s_warp[lane][1] : 0u, v2 = lane < NW ? s_warp[lane][2] : 0u, v3 = lane < NW ? s_warp[lane][3] : 0u;
+        const unsigned int v4 = lane < NW ? s_warp[lane][4] : 0u, v5 = lane < NW ? s_warp[lane][5] : 0u;
+        const unsigned int s1 = __reduce_add_sync(0xffffffffu, v1), s2 = __reduce_add_sync(0xffffffffu, v2 & 0xFFFFu);
+        const unsigned int s2b = __reduce_add_sync(0xffffffffu, v2 >> 16), s3 = __reduce_add_sync(0xffffffffu, v3);
+        const unsigned int s4 = __reduce_add_sync(0xffffffffu, v4), s5 = __reduce_max_sync(0xffffffffu, v5);
+        if (lane == 0) {
+            s_base_out = alive_total ? atomicAdd(P.n_out, alive_total) : 0u;
+            if (s1) atomicAdd(&P.stats->rays_shadow, (unsigned long long)s1);
+            if (s2) atomicAdd(&P.stats->misses, (unsigned long long)s2);
+            if (s2b) atomicAdd(&P.stats->truncated, (unsigned long long)s2b);
+            if (s3) atomicAdd(&P.stats->shaded, (unsigned long long)s3);
+            if (s4) atomicAdd(&P.stats->rays_scatter, (unsigned long long)s4);
+            if (s5 > *(volatile unsigned int *)&P.stats->max_depth_seen) atomicMax(&P.stats->max_depth_seen, s5);
         }
-        s_base_gen = g0;
-        s_regen_ok = ok;
-        const unsigned int n_out = alive_total + ok;
-        s_base_out = n_out ? atomicAdd(P.n_out, n_out) : 0u;
-        if (s_stat[0]) atomicAdd(&P.stats->rays_shadow, (unsigned long long)s_stat[0]);
-        if (s_stat[1]) atomicAdd(&P.stats->misses, (unsigned long long)s_stat[1]);
-        if (s_stat[2]) atomicAdd(&P.stats->truncated, (unsigned long long)s_stat[2]);
-        if (s_stat[3]) atomicAdd(&P.stats->shaded, (unsigned long long)s_stat[3]);
-        if (alive_total) atomicAdd(&P.stats->rays_scatter, (unsigned long long)alive_total);
-        if (s_stat[5] > 0) atomicMax(&P.stats->max_depth_seen, s_stat[5]);
     }
     __syncthreads();
-    const unsigned int lt = (1u << lane) - 1u;
-    const unsigned int rank_alive = alive_before + __popc(b_alive & lt);
-    const unsigned int rank_want = want_before + __popc(b_want & lt);
-    unsigned int slot = s_base_out + rank_alive;
-    if (want && rank_want < s_regen_ok) {
-        // ---- ray generation with uniform sub-pixel jitter (:533-536)
-        // path g -> (sample, owned pixel): pixel-major inside a sample so neighbouring lanes are neighbouring pixels
-        const unsigned long long g = s_base_gen + rank_want;
-        unsigned int sidx = (unsigned int)__double2uint_rz(__ull2double_rz(g) * P.inv_owned_pixels);
-        long long r = (long long)(g - (unsigned long long)sidx * P.owned_pixels);
-        if (r < 0) { sidx--; r += P.owned_pixels; }
-        else if (r >= (long long)P.owned_pixels) { sidx++; r -= P.owned_pixels; }
-        const unsigned int lp = (unsigned int)r;
-        unsigned int row_local, tile;
-        if (P.use_magic) {               // multiply-shift division (warp-uniform branch)
-            row_local = (unsigned int)(((unsigned long long)lp * P.magic_w) >> 40);
-            tile = (unsigned int)(((unsigned long long)row_local * P.magic_tile) >> 40);
-        } else {
-            row_local = lp / (unsigned int)P.w;
-            tile = row_local / (unsigned int)P.tile_rows;
-        }
-        const unsigned int xpix = lp - row_local * (unsigned int)P.w;
-        const unsigned int y = (tile * (unsigned int)P.world + (unsigned int)P.rank) * (unsigned int)P.tile_rows
-                             + (row_local - tile * (unsigned int)P.tile_rows);
-        pix = y * (unsigned int)P.w + xpix;
-        smp = sidx;
-        const uint4 rj = philox4x32_10(pix, smp, 0u, PT_DRAW_A, P.seed_lo, P.seed_hi);
-        const float u = ((float)xpix - 0.5f + u01(rj.x)) * P.inv_w;                            // :533
-        const float v = ((float)(P.h - 1 - (int)y) - 0.5f + u01(rj.y)) * P.inv_h;              // :534
-        F3 dc = f3(fmaf(P.cam_h[0], u, fmaf(P.cam_v[0], v, P.cam_base[0])),
-                   fmaf(P.cam_h[1], u, fmaf(P.cam_v[1], v, P.cam_base[1])),
-                   fmaf(P.cam_h[2], u, fmaf(P.cam_v[2], v, P.cam_base[2])));                    // :276-279
-        d = normalize3(dc);                                                                    // :536
-        o = f3(P.cam_o[0], P.cam_o[1], P.cam_o[2]);
-        T = f3(1.f, 1.f, 1.f);
-        L = f3(0.f, 0.f, 0.f);
-        depth = 0; prev = -1; E = 1;
-        alive = true;
-        slot = s_base_out + alive_total + rank_want;
-    }
     if (alive) {
+        const unsigned int slot = s_base_out + alive_before + __popc(b_alive & lt);
         P.qout[0][slot] = make_float4(o.x, o.y, o.z, __uint_as_float(pix));
         P.qout[1][slot] = make_float4(d.x, d.y, d.z, __uint_as_float(smp));
         P.qout[2][slot] = make_float4(T.x, T.y, T.z, __uint_as_float(pack_state(depth, prev, E)));
         if (STATS) P.qout[3][slot] = make_float4(L.x, L.y, L.z, 0.f);
     }
-
-}
-
-// marks every slot of a queue as dead (depth field = 0xFFFF) so the first bounce regenerates it
-__global__ void k_mark_dead(float4 *q2, unsigned int n)
-{
-    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) q2[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(PT_DEPTH_DEAD));
 }
 
 // fixed point -> double sums, restricted to the rows this rank owns (foreign rows stay zero)
@@ -556,19 +628,23 @@ __global__ void k_resolve(const unsigned long long *__restrict__ fix, const unsi
 
 // pt_debug_intersect, precision 32
 __global__ void k_intersect_fp32(const double *__restrict__ rays, int n_rays, double *__restrict__ t_out, int *__restrict__ id_out,
-                                 const MatF32 *__restrict__ mats)
+                                 const MatF32 *__restrict__ mats, const float4 *__restrict__ sphf)
 {
+    __shared__ float4 s_sphf[2 * (PT_MAX_OBJ + 4)];
+    for (int k = threadIdx.x; k < c_scene.n_sph4; k += blockDim.x) { s_sphf[k] = sphf[k]; s_sphf[PT_MAX_OBJ + 4 + k] = sphf[PT_MAX_OBJ + 4 + k]; }
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rays) return;
     const double *r = rays + (size_t)i * 6;
     F3 o = f3((float)r[0], (float)r[1], (float)r[2]), d = f3((float)r[3], (float)r[4], (float)r[5]);
     float t; int code;
-    closest_hit(o, d, -1, t, code);
+    closest_hit(o, d, -1, s_sphf, t, code);
     int id = -1;
     if (code >= 0) {
         // report the t the shading stage uses (refined once for the winning object) and the scene id
         const MatF32 m = mats[code];
-        t = refine_t(o, d, t, __float_as_int(m.e_type.w), m.geom, m.aux);
+        F3 x;
+        refine_hit(o, d, t, __float_as_int(m.e_type.w), m.geom, m.aux, x);
         id = __float_as_int(m.aux.w);
     }
     t_out[i] = id >= 0 ? (double)t : 1e20;
@@ -616,6 +692,9 @@ static int ensure_queues(pt_ctx *ctx, int capacity, bool stats)
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < (stats ? 4 : 3); b++)
             PT_CUDA(ctx, cudaMalloc(&ctx->q[a][b], sizeof(float4) * (size_t)capacity));
+    if (ctx->d_warp_chunk) cudaFree(ctx->d_warp_chunk);
+    ctx->d_warp_chunk = nullptr;
+    PT_CUDA(ctx, cudaMalloc(&ctx->d_warp_chunk, sizeof(uint4) * (size_t)(capacity / 32)));
     ctx->q_capacity = capacity;
     return PT_OK;
 }
@@ -649,21 +728,18 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
     PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fix, 0, n_acc * sizeof(unsigned long long), s));
     if (stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fixsq, 0, n_acc * sizeof(unsigned long long), s));
 
+    int it_total = 0;
     if (owned_pixels > 0 && p->spp > 0) {
         const unsigned long long total = owned_pixels * (unsigned long long)p->spp;
-        // queue capacity: default keeps both ping-pong queues inside L2 (48 B/path/queue)
+        // queue capacity = path slots in flight = threads per launch.  Default: PT_DEFAULT_WAVES full waves of resident
+        // blocks (no launch ends with a partially filled wave); the queues are touched once per launch, not per bounce.
         int cap = p->queue_capacity;
-        if (cap <= 0) {
-            // whole waves of resident blocks (4 blocks of 256 threads per SM, __launch_bounds__(256, 4)) so that no
-            // launch ends with a partially filled wave, as many as keep both queues within 3/4 of L2
-            const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
-            long long budget = (long long)ctx->l2_bytes * 3 / 4;
-            if (budget <= 0) budget = 64ll << 20;
-            long long waves = budget / (2 * (stats ? 64 : 48)) / wave;
-            if (waves < 2) waves = 2;
-            cap = (int)(waves * wave);
+        const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
+        if (cap <= 0) cap = (int)(PT_DEFAULT_WAVES * wave);
+        {   // never more slots than paths (rounded up to whole blocks)
+            const unsigned long long need = (total + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
+            if ((unsigned long long)cap > need) cap = (int)need;
         }
-        if ((unsigned long long)cap > total) cap = (int)total;
         cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
         int rc = ensure_queues(ctx, cap, stats);
         if (rc) return rc;
@@ -683,14 +759,22 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             if (dirty > (size_t)ctx->counts_len) dirty = (size_t)ctx->counts_len;
             PT_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned int) * dirty, s));
         }
-        unsigned int cap_u = (unsigned int)cap;
-        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_counts + 2, &cap_u, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+        PT_CUDA(ctx, cudaMemsetAsync(ctx->d_warp_chunk, 0, sizeof(uint4) * (size_t)(cap / 32), s));   // n[0] = 0: every slot starts without a path
         PT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_scene, ctx->h_scene32, sizeof(SceneF32), 0, cudaMemcpyHostToDevice, s));
-        k_mark_dead<<<(cap + 255) / 256, 256, 0, s>>>(ctx->q[0][2], cap_u);
-        ctx->stats.kernel_launches++;
 
         KParams P{};
         P.gen_counter = (unsigned long long *)ctx->d_counts;
+        P.warp_chunk = ctx->d_warp_chunk;
+        P.iters = p->bounces_per_launch > 0 ? p->bounces_per_launch : PT_DEFAULT_ITERS;
+        P.iters_tail = P.iters < PT_DEFAULT_ITERS_TAIL ? P.iters : PT_DEFAULT_ITERS_TAIL;
+        P.iters_drain = p->bounces_per_launch > 0 ? P.iters : PT_DEFAULT_ITERS_DRAIN;
+        P.drain_below = (unsigned int)(wave / 4);
+        {   // indices a warp reserves per atomic: enough for about one launch, but small renders still spread over the GPU
+            unsigned long long c = total / ((unsigned long long)(cap / 32) * 2ull);
+            unsigned int chunk = 32;
+            while (chunk < 256 && chunk * 2ull <= c) chunk *= 2;
+            P.chunk = chunk;
+        }
         P.total_paths = total;
         P.owned_pixels = (unsigned int)owned_pixels;
         P.inv_owned_pixels = 1.0 / (double)owned_pixels;
@@ -710,7 +794,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
-        P.mats = ctx->d_mats; P.stats = ctx->d_stats;
+        P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
 
         const int blocks = cap / PT_BLOCK;
         unsigned int *n_it = ctx->d_counts + 2;
@@ -719,7 +803,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         unsigned int *h_n = ctx->h_pinned;                 // pinned slots + events live in the context
         cudaEvent_t *evb = ctx->ev_batch;
         int it = 0, nb = 0, rc2 = PT_OK;
-        const int batch = 32;
+        const int batch = 4;
         bool done = false;
         while (!done) {
             for (int b = 0; b < batch && rc2 == PT_OK; b++, it++) {
@@ -748,10 +832,20 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         if (rc2 != PT_OK) { cudaStreamSynchronize(s); return rc2; }
         ctx->stats.iterations = (uint64_t)it;
         ctx->counts_dirty = (size_t)it + 4;
+        it_total = it;
     }
     k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc);
     ctx->stats.kernel_launches++;
     PT_CUDA(ctx, cudaGetLastError());
+    ctx->stats.queue_slots_io = 0;
+    if (it_total > 0) {   // queue traffic of this render: launch k reads n[k] slots and writes n[k+1]
+        std::vector<unsigned int> h(it_total + 1);
+        PT_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts + 2, sizeof(unsigned int) * (size_t)(it_total + 1), cudaMemcpyDeviceToHost, s));
+        PT_CUDA(ctx, cudaStreamSynchronize(s));
+        uint64_t io = 0;
+        for (int k = 0; k <= it_total; k++) io += (k == 0 || k == it_total) ? h[k] : 2ull * h[k];
+        ctx->stats.queue_slots_io = io;
+    }
     return PT_OK;
 }
 
@@ -759,7 +853,7 @@ int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int
 {
     if (!ctx->fp32_ok) return pt_fail(ctx, PT_ERR_ARG, "scene does not fit the FP32 engine: " + ctx->fp32_why);
     PT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_scene, ctx->h_scene32, sizeof(SceneF32), 0, cudaMemcpyHostToDevice, s));
-    k_intersect_fp32<<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats);
+    k_intersect_fp32<<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats, ctx->d_sphf);
     PT_CUDA(ctx, cudaGetLastError());
     return PT_OK;
 }

@@ -6,13 +6,17 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     from _pkg import ptb
     if os.environ.get("PTB200_LIB"):
         ptb.capi.LIB_PATH = os.environ["PTB200_LIB"]
-    sc = ptb.builtin_scene("A", 512, 512)
-    with ptb.Context(sc) as c:
-        best = 1e9
-        for _ in range(6):
-            c.render(ptb.params(512, 512, 512, mode=0))
-            st = c.stats(); best = min(best, st.render_ms)
-        print(json.dumps({"ms": best, "mpaths": st.paths / best * 1e-3, "its": st.iterations}))
+    res = {}
+    for name, (scene, w, h, spp, mode) in {"c2": ("A", 512, 512, 512, 0), "c1x8": ("A", 512, 512, 128, 1), "Bcos": ("B", 512, 512, 128, 1),
+                                            "c4/8": ("synthetic", 1920, 1080, 32, 1), "c5/16": ("A", 3840, 2160, 64, 0)}.items():
+        sc = ptb.builtin_scene(scene, w, h)
+        with ptb.Context(sc) as c:
+            best = 1e9
+            for _ in range(4):
+                c.render(ptb.params(w, h, spp, mode=mode))
+                st = c.stats(); best = min(best, st.render_ms)
+            res[name] = "%.2f ms %.0f Mp/s" % (best, st.paths / best * 1e-3)
+    print(json.dumps(res))
 else:
     libs = [""] + sorted(os.path.join(ROOT, "expt", f) for f in os.listdir(os.path.join(ROOT, "expt")) if f.endswith(".so"))
     for lib in libs:
