@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(ptb.Camera) == 96
     assert C.sizeof(ptb.Light) == 8 + 48
     assert C.sizeof(ptb.RenderParams) == 24 + 8 + 16 + 16
-    assert C.sizeof(ptb.Stats) == 72 + 8 + 16
+    assert C.sizeof(ptb.Stats) == 72 + 8 + 16 + 8
 
 
 def test_version_string():
