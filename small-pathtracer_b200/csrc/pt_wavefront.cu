@@ -45,10 +45,10 @@ namespace {
 #define PT_BLOCKS_PER_SM (1024 / PT_BLOCK)   /* 4 blocks of 256: 64 registers/thread keep the bounce loop's state out of local memory */
 #endif
 #ifndef PT_DEFAULT_WAVES
-#define PT_DEFAULT_WAVES 4
+#define PT_DEFAULT_WAVES 6
 #endif
 #ifndef PT_DEFAULT_ITERS
-#define PT_DEFAULT_ITERS 16         /* bounces per launch while camera paths are being generated */
+#define PT_DEFAULT_ITERS 32         /* bounces per launch while camera paths are being generated */
 #endif
 #ifndef PT_DEFAULT_ITERS_TAIL
 #define PT_DEFAULT_ITERS_TAIL 2     /* ... once generation is exhausted (compaction pays in the tail) ... */
