@@ -141,7 +141,7 @@ typedef struct pt_stats {
     uint64_t kernel_launches;   /* CUDA kernels launched by the last pt_render           */
     uint64_t iterations;        /* wavefront iterations of the last pt_render            */
     uint32_t max_depth_seen;
-    uint32_t _pad;
+    uint32_t specialised;       /* 1 = the last FP32 render ran the scene-specialised (NVRTC) build of k_bounce */
     double   render_ms;         /* device time of the last pt_render (CUDA events)       */
     double   main_kernel_ms;    /* summed device time of the dominant kernel             */
     uint64_t queue_slots_io;    /* path records read + written through the wavefront queues */
@@ -205,6 +205,19 @@ int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n
 /* FFMA-only microbenchmark: measured FP32 issue peak of this device in TFLOP/s
  * (FMA = 2 FLOPs), the denominator of the FP32 roofline. */
 int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
+
+/* Scene specialisation of the FP32 engine.  The reference's scene is a source literal (src/smallpt.cpp:287-311), so
+ * its compiler folds every plane constant; pt_render does the same for an uploaded scene by compiling, with NVRTC,
+ * a build of the bounce kernel in which the scene's rectangle constants and primitive counts are immediates (cached
+ * per scene and mode for the life of the process; ~1 s the first time, outside the timed region).
+ * mode: 0 = never (generic kernel, scene in __constant__ memory), 1 = for renders of >= 2^25 paths (default; the
+ * environment variable PTB200_JIT overrides the default), 2 = always.  pt_stats.specialised reports what ran. */
+int pt_set_specialisation(pt_ctx *ctx, int mode);
+
+/* Host-only (no device needed): the specialisation header generated for `scene` and render mode `mode`, and the
+ * size of the sm_100a cubin NVRTC builds from it.  spec_out/cubin_bytes/seconds may be NULL. Test entry. */
+int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t spec_cap, size_t *cubin_bytes,
+                        double *seconds);
 
 void        pt_destroy(pt_ctx *ctx);
 const char *pt_last_error(pt_ctx *ctx);   /* ctx may be NULL: last error of a failed upload */

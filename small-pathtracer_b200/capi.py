@@ -65,7 +65,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_camera", C.c_uint64), ("rays_scatter", C.c_uint64),
                 ("rays_shadow", C.c_uint64), ("shaded_vertices", C.c_uint64), ("miss_events", C.c_uint64),
                 ("truncated", C.c_uint64), ("kernel_launches", C.c_uint64), ("iterations", C.c_uint64),
-                ("max_depth_seen", C.c_uint32), ("_pad", C.c_uint32),
+                ("max_depth_seen", C.c_uint32), ("specialised", C.c_uint32),
                 ("render_ms", C.c_double), ("main_kernel_ms", C.c_double), ("queue_slots_io", C.c_uint64)]
 
     def as_dict(self):
@@ -235,7 +235,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_ffma_peak",
-           "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_debug_specialise", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -256,6 +256,8 @@ def lib():
         L.pt_debug_erand48.argtypes = [vp, C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.pt_debug_philox.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
         L.pt_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.pt_set_specialisation.argtypes = [vp, C.c_int]
+        L.pt_debug_specialise.argtypes = [C.POINTER(SceneDesc), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
         L.pt_destroy.argtypes = [vp]
         L.pt_destroy.restype = None
         L.pt_last_error.argtypes = [vp]
@@ -267,6 +269,18 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def specialise(scene, mode=PT_MODE_NEE_REF_RECT):
+    """Host-only: (specialisation header text, cubin bytes, NVRTC seconds) for `scene` — no GPU needed."""
+    d = scene.desc()
+    buf = C.create_string_buffer(1 << 16)
+    nbytes, secs = C.c_size_t(0), C.c_double(0)
+    rc = lib().pt_debug_specialise(C.byref(d), mode, buf, len(buf), C.byref(nbytes), C.byref(secs))
+    if rc:
+        msg = lib().pt_last_error(None)
+        raise PtError(f"pt_debug_specialise failed ({rc}): {msg.decode() if msg else ''}")
+    return buf.value.decode(), nbytes.value, secs.value
 
 
 class Context:
@@ -292,6 +306,10 @@ class Context:
         if rc:
             msg = lib().pt_last_error(self._h)
             raise PtError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def set_specialisation(self, mode):
+        """0 = generic kernel, 1 = scene-specialised (NVRTC) kernel for big renders (default), 2 = always."""
+        self._check(lib().pt_set_specialisation(self._h, mode), "pt_set_specialisation")
 
     def render(self, p):
         self.last = p

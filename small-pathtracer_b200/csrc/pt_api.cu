@@ -1,6 +1,7 @@
 // pt_api.cu — the extern "C" boundary of libptb200.so (include/ptb200.h): context, scene upload,
 // render dispatch, readback, debug entries.  No torch types, plain pointers and sizes.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -272,6 +273,7 @@ int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
     UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[0], cudaEventDisableTiming));
     UP_CUDA(cudaEventCreateWithFlags(&ctx->ev_batch[1], cudaEventDisableTiming));
 #undef UP_CUDA
+    if (const char *e = std::getenv("PTB200_JIT")) ctx->jit_mode = std::atoi(e) < 0 ? 0 : std::atoi(e) > 2 ? 2 : std::atoi(e);
     ctx->h_scene32 = new (std::nothrow) SceneF32;
     if (!ctx->h_scene32) { pt_destroy(ctx); return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed"); }
     int rc = upload_tables(ctx);
@@ -310,6 +312,12 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->last = *p;
     ctx->rendered = false;
+    ctx->jit = nullptr;
+    if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode > 0) {
+        // scene-specialised kernel: built (once per scene/mode) BEFORE the timed region starts
+        const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp / (unsigned long long)world;
+        if (ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS) ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0);
+    }
     PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, p->collect_stats ? ctx->d_sumsq : nullptr, s)
                                                  : pt_fp32_render(ctx, p, d_sum, ctx->d_sumsq, s);
@@ -324,6 +332,7 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     st.render_ms = ms;
     st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
     st.shaded_vertices = ds.shaded; st.max_depth_seen = ds.max_depth_seen;
+    st.specialised = ctx->jit ? 1u : 0u;
     if (p->engine == PT_ENGINE_FP64_ERAND48) {
         st.paths = ds.paths; st.rays_camera = ds.rays_camera; st.rays_scatter = ds.rays_scatter;
     } else {
@@ -340,6 +349,43 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
 }
 
 int pt_render(pt_ctx *ctx, const pt_render_params *p) { return render_common(ctx, p, nullptr, nullptr); }
+
+int pt_set_specialisation(pt_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return pt_fail(ctx, PT_ERR_ARG, "specialisation mode must be 0, 1 or 2");
+    ctx->jit_mode = mode;
+    return PT_OK;
+}
+
+int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t spec_cap, size_t *cubin_bytes, double *seconds)
+{
+    // host only: flatten + class-sort the scene exactly as pt_scene_upload does, then run NVRTC (no device needed)
+    if (!scene) return pt_fail(nullptr, PT_ERR_ARG, "null argument");
+    pt_ctx tmp;
+    std::string why;
+    if (flatten_scene(scene, tmp.objs, why) != PT_OK) return pt_fail(nullptr, PT_ERR_ARG, why);
+    tmp.cam = scene->camera;
+    tmp.light = scene->light;
+    std::vector<MatF32> mats;
+    SceneF32 *S = new (std::nothrow) SceneF32;
+    if (!S) return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed");
+    tmp.h_scene32 = S;
+    build_scene_f32(&tmp, mats);
+    int rc = PT_OK;
+    if (!tmp.fp32_ok) rc = pt_fail(nullptr, PT_ERR_ARG, "scene does not fit the FP32 engine: " + tmp.fp32_why);
+    else {
+        const std::string spec = pt_jit_spec(*S, mode, false);
+        if (spec_out && spec_cap) { std::strncpy(spec_out, spec.c_str(), spec_cap - 1); spec_out[spec_cap - 1] = 0; }
+        std::vector<char> cubin;
+        std::string log;
+        rc = pt_jit_compile(spec, cubin, log, seconds);
+        if (rc != PT_OK) rc = pt_fail(nullptr, rc, "NVRTC: " + log);
+        else if (cubin_bytes) *cubin_bytes = cubin.size();
+    }
+    tmp.h_scene32 = nullptr;
+    delete S;
+    return rc;
+}
 
 int pt_render_into(pt_ctx *ctx, const pt_render_params *p, void *dev_rgb_sum, void *stream)
 {

@@ -9,9 +9,9 @@
 #include <vector>
 
 #include "ptb200.h"
+#include "pt_scene_dev.h"
 
 // ------------------------------------------------------------------ FP64 engine scene (global memory)
-enum { OT_SPHERE = 0, OT_XZ = 1, OT_XY = 2, OT_YZ = 3, OT_TILT = 4 };
 
 struct DevObj64 {
     int    type, refl;
@@ -22,61 +22,10 @@ struct DevObj64 {
     double p0[3], n[3], s[3], t[3], hs, ht;
 };
 
-// ------------------------------------------------------------------ FP32 engine scene
-#define PT_MAX_OBJ        512     // objects the FP32 constant-memory layout holds
-#define PT_MAX_HUGE       64
-#define PT_MAX_TILT       64
-#define PT_HUGE_RADIUS    100.0   // spheres at least this big take the FP64 c-term path
-
-#define PT_SPH_KAPPA      3.814697265625e-6f   /* 2^-18: relative slack of the conservative sphere scan */
-
-#define PT_RECT_SLOTS     16      // rectangles per axis class tested by fully unrolled, constant-operand code
-
-// The FP32 engine addresses objects by CODE (position in the class-sorted layout), not by scene id:
-//   [0, 48)                         unrolled rectangle slots, code = axis*16 + k   (axis: XZ 0, XY 1, YZ 2)
-//   [48, 48 + n_ovf)                overflow rectangles (generic loop), axis by axis
-//   [code_sph0, +n_sph)             small spheres        [code_huge0, +n_huge)  huge spheres
-//   [code_tilt0, +n_tilt)           tilted planes
-// Within a class codes ascend with scene id, so "lowest id wins ties" (src/smallpt.cpp:328) holds per class.
-struct SceneF32 {                 // lives in __constant__ memory: every access is warp-uniform
-    int   n_slot[3];              // rectangles in the unrolled slots of each axis class (<= PT_RECT_SLOTS)
-    int   ovf_begin[4];           // [axis] .. [axis+1): overflow entries of rect_a / rect_b2
-    int   n_sph, n_huge, n_tilt;
-    int   code_sph0, code_huge0, code_tilt0, n_codes;
-    int   code_obj0;              // code of scene object 0 (where a missed ray "lands", :373-374)
-    // NEE_REF_RECT light (src/smallpt.cpp:365-367,467,471)
-    int   light_code;
-    float lx0, lxw, lz0, lzw, ly, larea;
-    int   n_lights;               // emissive spheres for NEE_CONE_SPHERE
-    int   light_sph_code[32];
-    float4 slot_a[3][PT_RECT_SLOTS];   // k, a1, a2 - a1, b1   (one 128-bit uniform load)
-    float  slot_b2[3][PT_RECT_SLOTS];  // b2 - b1
-    float4 rect_a[PT_MAX_OBJ];    // overflow rectangles: k, a1, a2, b1
-    float  rect_b2[PT_MAX_OBJ];   //                      b2
-    float4 sph[PT_MAX_OBJ];       // c.x, c.y, c.z, rad^2
-    // conservative scan form of the same spheres (see closest_hit): centres relative to sph_c, w = |c'|^2 - rad^2;
-    // padded to a multiple of 4 with entries that can never pass (w = 3e38)
-    float4 sphf[PT_MAX_OBJ + 4];
-    float  sph_c[3];              // translation that centres the small spheres around the origin
-    float  sph_kM2;               // PT_SPH_KAPPA * max_i (|c'_i| + rad_i)^2
-    int    n_sph4;                // n_sph rounded up to a multiple of 4
-    double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64
-    float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
-};
-
-struct MatF32 {                   // global memory, indexed by CODE (divergent index, so NOT constant memory)
-    float4 c_refl;                // c.xyz, refl (int bits)
-    float4 e_type;                // e.xyz, type (int bits)
-    float4 geom;                  // sphere: centre.xyz, 1/rad ; rect: k_hi, k_lo (k = hi + lo), -, - ; tilted: n.xyz
-    float4 aux;                   // tilted: p0.xyz ; .w = scene id (int bits)
-};
-
-struct DevStats {                 // device-side counters (unsigned long long for atomicAdd)
-    unsigned long long paths, rays_camera, rays_scatter, rays_shadow, shaded, misses, truncated;
-    unsigned int max_depth_seen, pad;
-};
-
 // ------------------------------------------------------------------ context
+struct PtJitKernel;
+#define PT_JIT_MIN_PATHS (1ull << 25)   /* renders at least this big are worth a ~1 s specialised build (jit_mode 1) */
+
 struct pt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -116,10 +65,24 @@ struct pt_ctx {
     size_t stage_elems = 0;
     DevStats *d_stats = nullptr;
     pt_stats stats{};
+    // scene specialisation: 0 = generic kernel only, 1 = specialise renders of >= PT_JIT_MIN_PATHS paths, 2 = always
+    int jit_mode = 1;
+    PtJitKernel *jit = nullptr;                        // kernel chosen for the render in flight (nullptr = generic)
+    std::string jit_note;
     std::string err;
 };
 
 int pt_fail(pt_ctx *ctx, int code, const std::string &msg);
+
+// scene-specialised kernels (pt_jit.cu)
+struct PtJitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    double compile_seconds = 0;
+};
+std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats);
+int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats);
 #define PT_CUDA(ctx, call)                                                                      \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \

@@ -1,0 +1,178 @@
+// pt_jit.cu — scene-specialised builds of k_bounce, compiled at run time with NVRTC for sm_100a.
+//
+// The reference hard-codes its scene as a source literal (src/smallpt.cpp:287-311): the compiler sees every plane
+// constant.  The generic k_bounce reads them from __constant__ memory (two uniform loads per rectangle, a jump-table
+// dispatch per axis class, run-time loop bounds).  Here the uploaded scene is turned back into source: a small header
+// of constexpr tables (rectangle slots as hex-float literals, primitive counts, light constants) is put in front of
+// the SAME kernel source (pt_kernel.cuh, embedded at build time) and compiled with PT_JIT defined, so the constants
+// become immediates, equal sub-expressions (o.x - a1 for slots that share a1) are computed once, and empty primitive
+// classes vanish.  One module per (scene constants, mode, statistics flag), cached for the life of the process.
+//
+// NVRTC is loaded with dlopen: the library has no link-time dependency on it and falls back to the ahead-of-time
+// generic kernel (still a GPU kernel, never a CPU path) when it is missing or the compilation fails.
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "pt_internal.h"
+#include "pt_kernel_src.h"
+
+namespace {
+
+struct Nvrtc {
+    void *h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+Nvrtc &nvrtc()
+{
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *env = std::getenv("PTB200_NVRTC");
+        const char *names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (n.h) break;
+        }
+        if (!n.h) { n.why = "libnvrtc not found"; return; }
+#define PT_SYM(f) *(void **)(&n.f) = dlsym(n.h, "nvrtc" #f); if (!n.f) { n.why = "nvrtc" #f " missing"; return; }
+        PT_SYM(CreateProgram) PT_SYM(CompileProgram) PT_SYM(GetCUBINSize) PT_SYM(GetCUBIN)
+        PT_SYM(GetProgramLogSize) PT_SYM(GetProgramLog) PT_SYM(DestroyProgram)
+#undef PT_SYM
+        n.ok = true;
+    });
+    return n;
+}
+
+void put_float(std::string &s, float v)
+{
+    char b[64];
+    if (v != v) std::snprintf(b, sizeof b, "__int_as_float(0x7fc00000)");
+    else if (v > 3.4e38f) std::snprintf(b, sizeof b, "__int_as_float(0x7f800000)");
+    else if (v < -3.4e38f) std::snprintf(b, sizeof b, "__int_as_float(0xff800000)");
+    else std::snprintf(b, sizeof b, "%af", (double)v);       // hex float: exact
+    s += b;
+}
+
+unsigned int float_bits(float v) { unsigned int u; std::memcpy(&u, &v, 4); return u; }
+
+std::mutex g_mu;
+std::map<std::string, PtJitKernel *> g_cache;       // key = specialisation header (contains mode and stats flag)
+
+}  // namespace
+
+// The specialisation header of a scene: everything k_bounce reads through PT_SC / PT_J_SLOT.
+std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
+{
+    std::string h;
+    char b[256];
+    std::snprintf(b, sizeof b, "#define PT_JIT 1\n#define PT_J_MODE %d\n#define PT_J_STATS %d\n", mode, stats ? 1 : 0);
+    h += b;
+    std::snprintf(b, sizeof b, "constexpr int PT_J_NSLOT[3] = {%d, %d, %d};\n#define PT_J_NOVF %d\n", S.n_slot[0], S.n_slot[1], S.n_slot[2], S.ovf_begin[3]);
+    h += b;
+    h += "constexpr float PT_J_SLOT[3][16][3] = {\n";         // k, a1, b1
+    for (int a = 0; a < 3; a++) {
+        h += " {";
+        for (int k = 0; k < PT_RECT_SLOTS; k++) {
+            h += "{"; put_float(h, S.slot_a[a][k].x); h += ","; put_float(h, S.slot_a[a][k].y); h += ","; put_float(h, S.slot_a[a][k].w); h += "},";
+        }
+        h += "},\n";
+    }
+    h += "};\nconstexpr unsigned int PT_J_SLOTB[3][16][2] = {\n";   // bits(a2 - a1), bits(b2 - b1)
+    for (int a = 0; a < 3; a++) {
+        h += " {";
+        for (int k = 0; k < PT_RECT_SLOTS; k++) {
+            std::snprintf(b, sizeof b, "{0x%08xu,0x%08xu},", float_bits(S.slot_a[a][k].z), float_bits(S.slot_b2[a][k]));
+            h += b;
+        }
+        h += "},\n";
+    }
+    h += "};\n";
+    auto def_i = [&](const char *n, int v) { std::snprintf(b, sizeof b, "#define PT_J_%s %d\n", n, v); h += b; };
+    auto def_f = [&](const char *n, float v) { h += "#define PT_J_"; h += n; h += " ("; put_float(h, v); h += ")\n"; };
+    def_i("n_sph4", S.n_sph4); def_i("n_huge", S.n_huge); def_i("n_tilt", S.n_tilt); def_i("n_lights", S.n_lights);
+    def_i("code_sph0", S.code_sph0); def_i("code_huge0", S.code_huge0); def_i("code_tilt0", S.code_tilt0);
+    def_i("code_obj0", S.code_obj0); def_i("light_code", S.light_code);
+    def_f("lx0", S.lx0); def_f("lxw", S.lxw); def_f("lz0", S.lz0); def_f("lzw", S.lzw); def_f("ly", S.ly); def_f("larea", S.larea);
+    def_f("sph_kM2", S.sph_kM2);
+    h += "constexpr float PT_J_sph_c[3] = {"; put_float(h, S.sph_c[0]); h += ","; put_float(h, S.sph_c[1]); h += ","; put_float(h, S.sph_c[2]); h += "};\n";
+    return h;
+}
+
+// NVRTC: specialisation header + embedded kernel source -> sm_100a cubin.  No GPU needed (unit-tested on CPU).
+int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds)
+{
+    Nvrtc &n = nvrtc();
+    if (!n.ok) { log = n.why; return PT_ERR_STATE; }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string src = spec;
+    src += PT_KERNEL_SRC;
+    nvrtcProgram prog = nullptr;
+    if (n.CreateProgram(&prog, src.c_str(), "pt_kernel_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return PT_ERR_STATE; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    const nvrtcResult rc = n.CompileProgram(prog, 4, opts);
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    if (ls > 1) { log.resize(ls); n.GetProgramLog(prog, &log[0]); }
+    if (rc != NVRTC_SUCCESS) { n.DestroyProgram(&prog); if (log.empty()) log = "nvrtcCompileProgram failed"; return PT_ERR_STATE; }
+    size_t cs = 0;
+    if (n.GetCUBINSize(prog, &cs) != NVRTC_SUCCESS || cs == 0) { n.DestroyProgram(&prog); log = "no cubin"; return PT_ERR_STATE; }
+    cubin.resize(cs);
+    n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    if (const char *dump = std::getenv("PTB200_JIT_DUMP")) {       // keep the cubin for cuobjdump -sass
+        if (FILE *f = std::fopen(dump, "wb")) { std::fwrite(cubin.data(), 1, cubin.size(), f); std::fclose(f); }
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return PT_OK;
+}
+
+// The specialised kernel for the context's current scene, or nullptr (generic kernel) when JIT is off/unavailable.
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats)
+{
+    if (!ctx->fp32_ok) return nullptr;
+    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(spec);
+    if (it != g_cache.end()) return it->second;          // may be nullptr: a failed build is not retried
+    PtJitKernel *jk = nullptr;
+    std::vector<char> cubin;
+    std::string log;
+    double secs = 0;
+    if (pt_jit_compile(spec, cubin, log, &secs) == PT_OK) {
+        jk = new PtJitKernel();
+        jk->compile_seconds = secs;
+        cudaError_t e = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+        if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk->kern, jk->lib, "k_bounce_jit");
+        if (e != cudaSuccess) {
+            log = std::string("loading the specialised module: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            delete jk;
+            jk = nullptr;
+        }
+    }
+    if (!jk) {
+        ctx->jit_note = "generic kernel (" + log.substr(0, 300) + ")";
+        if (std::getenv("PTB200_JIT_VERBOSE")) std::fprintf(stderr, "[ptb200] JIT unavailable: %s\n", log.c_str());
+    } else if (std::getenv("PTB200_JIT_VERBOSE")) {
+        std::fprintf(stderr, "[ptb200] scene-specialised k_bounce (mode %d) compiled in %.2f s\n", mode, secs);
+    }
+    g_cache[spec] = jk;
+    return jk;
+}

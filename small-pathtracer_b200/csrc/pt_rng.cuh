@@ -6,7 +6,9 @@
 #ifndef PT_RNG_CUH
 #define PT_RNG_CUH
 
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #define PT_PHILOX_M0 0xD2511F53u
 #define PT_PHILOX_M1 0xCD9E8D57u

@@ -1,0 +1,39 @@
+"""CPU: the scene-specialisation front end (pt_jit.cu).  NVRTC needs no GPU: the header generated for a scene must
+carry the scene's constants and compile to an sm_100a cubin; a scene that differs in one constant gives another header."""
+import re
+
+import pytest
+
+from conftest import ptb
+
+
+def _have_nvrtc():
+    try:
+        ptb.specialise(ptb.builtin_scene("C", 64, 64), 1)
+        return True
+    except ptb.PtError as e:
+        return "libnvrtc not found" not in str(e) and pytest.fail(str(e))
+
+
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+@pytest.mark.parametrize("scene,mode", [("A", 0), ("B", 1), ("synthetic", 2), ("B", 3)])
+def test_specialised_source_compiles_for_sm100a(scene, mode):
+    spec, cubin_bytes, seconds = ptb.specialise(ptb.builtin_scene(scene, 128, 96), mode)
+    assert f"#define PT_J_MODE {mode}" in spec
+    assert cubin_bytes > 10000
+    assert seconds < 60
+
+
+def test_header_carries_the_scene_constants():
+    sc = ptb.builtin_scene("A", 64, 64)
+    spec, _, _ = ptb.specialise(sc, 0)
+    # scene A (src/smallpt.cpp:287-311): 5 XZ, 6 XY and 6 YZ rectangles, no spheres, light = object 6 (the third XZ slot)
+    assert "constexpr int PT_J_NSLOT[3] = {5, 6, 6};" in spec
+    assert "#define PT_J_n_sph4 0" in spec and "#define PT_J_n_tilt 0" in spec
+    assert "#define PT_J_light_code 2" in spec
+    # k = 81.6 and 81.5 as exact FP32 hex floats, the ceiling and the light
+    assert float.fromhex("0x1.466666p+6") == pytest.approx(81.6, rel=1e-7) and "0x1.466666p+6f" in spec and "0x1.46p+6f" in spec
+    # light sampling constants of :365-367 (32 + 36 xi, 63 + 36 xi, y = 81.6, A = 1296)
+    assert re.search(r"#define PT_J_lxw \(0x1\.2p\+5f\)", spec) and re.search(r"#define PT_J_larea \(0x1\.44p\+10f\)", spec)
+    other, _, _ = ptb.specialise(ptb.builtin_scene("C", 64, 64), 0)
+    assert other != spec

@@ -6,5 +6,5 @@ NAME=$1; shift
 mkdir -p expt build
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Ismall-pathtracer_b200/csrc -Xptxas -v $@ \
      -c small-pathtracer_b200/csrc/pt_wavefront.cu -o build/pt_wavefront_$NAME.o 2> build/v_$NAME.log
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static build/pt_validate.o build/pt_wavefront_$NAME.o build/pt_api.o -o expt/libptb200_$NAME.so
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static build/pt_validate.o build/pt_wavefront_$NAME.o build/pt_api.o build/pt_jit.o -ldl -o expt/libptb200_$NAME.so
 grep -A2 "k_bounceILi[01]ELb0" build/v_$NAME.log | grep "spill\|Used" | tr '\n' ' '; echo
