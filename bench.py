@@ -167,6 +167,7 @@ def secondary(ptb, workload, peak_tf, device_index, stream, flush):
         tf = flops / (best.render_ms * 1e-3) / 1e12
         return {"workload": desc, "value": best.paths / best.render_ms * 1e-3, "unit": METRIC, "mrays_per_s": best.rays / best.render_ms * 1e-3,
                 "ms_per_step": best.render_ms, "rays_per_path": best.rays / best.paths, "launches_per_step": int(best.iterations),
+                "specialised": bool(best.specialised),
                 "roofline": {"bound": "fp32", "kernel": "k_bounce", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                              "flops_per_ray": scene.flops_per_ray(), "flops_per_bounce": F_SHADE[mode]}}
 
@@ -352,7 +353,10 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "engine": "FP32 Philox wavefront", "tile_rows": tile_rows, "parallelism": f"row-tiles x{world}",
                        "l2": "256 MiB flush write between timed iterations", "paths_per_step": paths / args.steps,
-                       "rays_per_path": rays / paths, "seed": 0},
+                       "rays_per_path": rays / paths, "seed": 0,
+                       "kernel": ("scene-specialised k_bounce (NVRTC build with the scene constants as immediates, compiled once during warm-up)"
+                                  if stats.specialised else "generic k_bounce (scene in __constant__ memory)"),
+                       "bounces_per_launch": 32},
             "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
             "clocks": clocks, "gpu_launches": int(launches_all),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -25,6 +25,9 @@
 // in FP64 and conjugate roots; the sphere a ray starts on is solved exactly (roots {0, 2b}).
 #include <math_constants.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "pt_internal.h"
 #include "pt_kernel.cuh"
 
@@ -196,7 +199,11 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.iters = p->bounces_per_launch > 0 ? p->bounces_per_launch : PT_DEFAULT_ITERS;
         P.iters_tail = P.iters < PT_DEFAULT_ITERS_TAIL ? P.iters : PT_DEFAULT_ITERS_TAIL;
         P.iters_drain = p->bounces_per_launch > 0 ? P.iters : PT_DEFAULT_ITERS_DRAIN;
-        P.drain_below = (unsigned int)(wave / 4);
+        P.drain_below = (unsigned int)wave;
+        // tuning overrides (tools/sweep_tail.py)
+        if (const char *e = std::getenv("PTB200_ITERS_TAIL")) P.iters_tail = std::atoi(e) > 0 ? std::atoi(e) : P.iters_tail;
+        if (const char *e = std::getenv("PTB200_ITERS_DRAIN")) P.iters_drain = std::atoi(e) > 0 ? std::atoi(e) : P.iters_drain;
+        if (const char *e = std::getenv("PTB200_DRAIN_BELOW")) P.drain_below = (unsigned int)std::atoi(e);
         {   // indices a warp reserves per atomic: enough for about one launch, but small renders still spread over the GPU
             unsigned long long c = total / ((unsigned long long)(cap / 32) * 2ull);
             unsigned int chunk = 32;
@@ -231,7 +238,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         unsigned int *h_n = ctx->h_pinned;                 // pinned slots + events live in the context
         cudaEvent_t *evb = ctx->ev_batch;
         int it = 0, nb = 0, rc2 = PT_OK;
-        const int batch = 4;
+        const int batch = std::getenv("PTB200_BATCH") ? std::max(1, std::atoi(std::getenv("PTB200_BATCH"))) : 2;
         bool done = false;
         while (!done) {
             for (int b = 0; b < batch && rc2 == PT_OK; b++, it++) {
