@@ -116,6 +116,7 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
         for (int k = S.n_sph; k < S.n_sph4; k++) S.sphf[k] = make_float4(0.f, 0.f, 0.f, 3.0e38f);
         S.sph_kM2 = (float)(PT_SPH_KAPPA * M2);
     }
+    for (int i = 0; i < n; i++) S.refl_mask |= 1 << ctx->objs[i].refl;
     S.code_obj0 = code_of[0];
     S.light_code = (ctx->light.id >= 0 && ctx->light.id < n) ? code_of[ctx->light.id] : -2;
     S.lx0 = (float)ctx->light.x0; S.lxw = (float)ctx->light.xw;
@@ -469,25 +470,29 @@ int pt_debug_erand48(pt_ctx *ctx, const uint16_t *seeds, int n_threads, int draw
     return PT_OK;
 }
 
-int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out)
+static int debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out, int width)
 {
     if (!ctx || !ctr || !key || !out || n <= 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nc = (size_t)width * n, nk = (size_t)(width / 2) * n;
     uint32_t *d_c = nullptr, *d_k = nullptr, *d_o = nullptr;
-    PT_CUDA(ctx, cudaMalloc(&d_c, sizeof(uint32_t) * 4 * (size_t)n));
-    PT_CUDA(ctx, cudaMalloc(&d_k, sizeof(uint32_t) * 2 * (size_t)n));
-    PT_CUDA(ctx, cudaMalloc(&d_o, sizeof(uint32_t) * 4 * (size_t)n));
-    cudaError_t e = cudaMemcpyAsync(d_c, ctr, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, key, sizeof(uint32_t) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    PT_CUDA(ctx, cudaMalloc(&d_c, sizeof(uint32_t) * nc));
+    PT_CUDA(ctx, cudaMalloc(&d_k, sizeof(uint32_t) * nk));
+    PT_CUDA(ctx, cudaMalloc(&d_o, sizeof(uint32_t) * nc));
+    cudaError_t e = cudaMemcpyAsync(d_c, ctr, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, key, sizeof(uint32_t) * nk, cudaMemcpyHostToDevice, ctx->stream);
     int rc = PT_OK;
-    if (e == cudaSuccess) rc = pt_fp32_philox(ctx, d_c, d_k, n, d_o, ctx->stream);
-    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(uint32_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) rc = pt_fp32_philox(ctx, d_c, d_k, n, d_o, ctx->stream, width);
+    if (rc == PT_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, ctx->stream);
     if (rc == PT_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_c); cudaFree(d_k); cudaFree(d_o);
     if (rc != PT_OK) return rc;
     if (e != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_debug_philox: ") + cudaGetErrorString(e));
     return PT_OK;
 }
+
+int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out) { return debug_philox(ctx, ctr, key, n, out, 4); }
+int pt_debug_philox2x32(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out) { return debug_philox(ctx, ctr, key, n, out, 2); }
 
 int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz)
 {

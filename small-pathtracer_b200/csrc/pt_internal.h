@@ -98,7 +98,7 @@ int pt_fp64_erand48(pt_ctx *ctx, const uint16_t *d_seeds, int n_threads, int dra
 
 int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double *d_sumsq, cudaStream_t s);
 int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int *d_id, cudaStream_t s);
-int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s);
+int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s, int width);
 int pt_fp32_ffma_peak(pt_ctx *ctx, double *tflops, double *mhz);
 
 #endif

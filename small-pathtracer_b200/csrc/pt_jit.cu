@@ -107,6 +107,9 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
     auto def_i = [&](const char *n, int v) { std::snprintf(b, sizeof b, "#define PT_J_%s %d\n", n, v); h += b; };
     auto def_f = [&](const char *n, float v) { h += "#define PT_J_"; h += n; h += " ("; put_float(h, v); h += ")\n"; };
     def_i("n_sph4", S.n_sph4); def_i("n_huge", S.n_huge); def_i("n_tilt", S.n_tilt); def_i("n_lights", S.n_lights);
+    def_i("has_sphere", (S.n_sph > 0 || S.n_huge > 0) ? 1 : 0); def_i("has_small_sphere", S.n_sph > 0 ? 1 : 0); def_i("has_tilt", S.n_tilt > 0 ? 1 : 0);
+    def_i("has_rect", (S.n_slot[0] + S.n_slot[1] + S.n_slot[2] + S.ovf_begin[3]) > 0 ? 1 : 0);
+    def_i("has_spec", (S.refl_mask >> PT_SPEC) & 1); def_i("has_refr", (S.refl_mask >> PT_REFR) & 1); def_i("has_diff", (S.refl_mask >> PT_DIFF) & 1);
     def_i("code_sph0", S.code_sph0); def_i("code_huge0", S.code_huge0); def_i("code_tilt0", S.code_tilt0);
     def_i("code_obj0", S.code_obj0); def_i("light_code", S.light_code);
     def_f("lx0", S.lx0); def_f("lxw", S.lxw); def_f("lz0", S.lz0); def_f("lzw", S.lzw); def_f("ly", S.ly); def_f("larea", S.larea);
@@ -124,7 +127,12 @@ int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::strin
     std::string src = spec;
     src += PT_KERNEL_SRC;
     nvrtcProgram prog = nullptr;
-    if (n.CreateProgram(&prog, src.c_str(), "pt_kernel_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return PT_ERR_STATE; }
+    std::string name = "pt_kernel_jit.cu";
+    if (const char *keep = std::getenv("PTB200_JIT_KEEP_SRC")) {   // write the translation unit where ncu --import-source finds it
+        name = keep;
+        if (FILE *f = std::fopen(keep, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
+    }
+    if (n.CreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return PT_ERR_STATE; }
     const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
     const nvrtcResult rc = n.CompileProgram(prog, 4, opts);
     size_t ls = 0;

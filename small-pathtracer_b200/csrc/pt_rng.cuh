@@ -31,6 +31,20 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Philox2x32-10: half the multiplies; the camera-ray jitter needs only two uniforms per path (:533-534).
+#define PT_PHILOX2_M 0xD256D193u
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi = __umulhi(PT_PHILOX2_M, c0), lo = PT_PHILOX2_M * c0;
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += PT_PHILOX_W0;
+    }
+    return make_uint2(c0, c1);
+}
+
 // [0,1) with 24 random bits (exact in FP32; never 1.0f)
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 

@@ -68,6 +68,14 @@ __global__ void k_intersect_fp32(const double *__restrict__ rays, int n_rays, do
     id_out[i] = id;
 }
 
+__global__ void k_philox2(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 r = philox2x32_10(ctr[2 * i], ctr[2 * i + 1], key[i]);
+    out[2 * i] = r.x; out[2 * i + 1] = r.y;
+}
+
 __global__ void k_philox(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,6 +236,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.cam_v[0] = (float)c.vertical.x; P.cam_v[1] = (float)c.vertical.y; P.cam_v[2] = (float)c.vertical.z;
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
+        P.seed_jitter = (P.seed_lo ^ (P.seed_hi * 0x85EBCA6Bu)) + 0xC2B2AE35u;
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
         P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
 
@@ -293,9 +302,10 @@ int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int
     return PT_OK;
 }
 
-int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s)
+int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s, int width)
 {
-    k_philox<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
+    if (width == 2) k_philox2<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
+    else k_philox<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
     PT_CUDA(ctx, cudaGetLastError());
     return PT_OK;
 }

@@ -102,7 +102,7 @@ def test_cone_light_sampling_is_unbiased(light):
     if light == "builtin":
         sc, n_cone, n_cos = ptb.builtin_scene("B", w, h), 2048, 4096
     else:
-        sc, n_cone, n_cos = _scene_B_with_light(1.5, (50, 81.6 - 16.5, 81.6), 400.0, w, h), 1024, 16384
+        sc, n_cone, n_cos = _scene_B_with_light(1.5, (50, 81.6 - 16.5, 81.6), 400.0, w, h), 2048, 65536
     with ptb.Context(sc) as c:
         c.render(ptb.params(w, h, n_cone, mode=ptb.PT_MODE_NEE_CONE_SPHERE, seed=1, collect_stats=1))
         m_cone, s_cone, st_cone = c.readback(True)

@@ -1,2 +1,4 @@
 set -x
-python tools/sweep_tail.py > gpurun_out/sweep_tail_s9.log 2>&1; cat gpurun_out/sweep_tail_s9.log
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_s12.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_gpu_s12.log
+python tools/abtest.py > gpurun_out/abtest_s12.log 2>&1; cat gpurun_out/abtest_s12.log
