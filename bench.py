@@ -293,28 +293,46 @@ def main():
     mrays = rays / total_ms * 1e-3
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
+    host_img = np.empty((h, w, 3), dtype=np.float64)                       # the caller's result buffer, re-used every step
+    host_pinned = torch.empty((h, w, 3), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
+
     def e2e_step():
         t0 = time.perf_counter()
         ctx.update_scene(scene)                                             # H2D: scene table + camera (pt_scene_upload, in place)
         if world > 1:
             full, local = pdist.render_sharded(ctx, params, device, dst=0)
-            host = full.cpu().numpy() if rank == 0 else None                # D2H: assembled image
+            host = None
+            if rank == 0:                                                   # D2H: assembled image (sum -> mean on the device)
+                host_pinned.copy_(full / float(spp), non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+                host = host_pinned.numpy()
         else:
             ctx.render(params)
-            host, _ = ctx.readback()                                        # D2H inside pt_readback
+            host, _ = ctx.readback(out=host_img)                            # D2H inside pt_readback
         if world > 1:
             dist.barrier()
         return time.perf_counter() - t0, host
     e2e_step()
     barrier()
     e2e_times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        dt, host_img = e2e_step()
+    for _ in range(max(1, min(args.steps, 10))):
+        dt, _img = e2e_step()
         e2e_times.append(dt)
     e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = (paths / args.steps) * len(e2e_times) / float(e2e_t[0]) * 1e-6
+    # strong-scaling reference measured in the same job: rank 0 renders the WHOLE workload alone (the other ranks wait)
+    single_ms = None
+    if world > 1:
+        if rank == 0:
+            p1 = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=0, world=1)
+            for _ in range(2):
+                flush.fill_(1)
+                stream.synchronize()
+                ctx.render(p1)
+                single_ms = ctx.stats().render_ms
+        dist.barrier()
     import ctypes as C
     h2d = scene.n_spheres * C.sizeof(ptb.Sphere) + scene.n_planes * C.sizeof(ptb.Plane) + 4 * scene.n_objects + C.sizeof(ptb.Camera) + C.sizeof(ptb.Light)
     d2h = w * h * 3 * 8
@@ -362,6 +380,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback (FP64 image device->host) per step, wall clock"},
             "roofline": roofline}
+    if single_ms:
+        line["strong_scaling"] = {"single_gpu_ms_per_step": single_ms, "n_gpu_ms_per_step": total_ms / args.steps,
+                                  "speedup": single_ms / (total_ms / args.steps), "n_gpus": n_gpus,
+                                  "note": "same workload rendered by rank 0 alone in this job (render only, no gather) vs the sharded step incl. gather"}
     if n_gpus == 1 and not args.no_secondary and workload == "c2":
         # the intersection-bound configuration (C4) next to the headline: same engine, same accounting
         try:

@@ -320,10 +320,16 @@ class Context:
         self.last = p
         self._check(lib().pt_render_into(self._h, C.byref(p), C.c_void_p(dev_ptr), C.c_void_p(stream)), "pt_render_into")
 
-    def readback(self, want_sumsq=False):
+    def readback(self, want_sumsq=False, out=None):
+        """Mean image (H, W, 3) float64 [+ sum of squares] + stats.  `out`: a caller-owned float64 array to fill (a
+        renderer that reads back every frame re-uses one buffer instead of faulting in fresh pages each time)."""
         p = self.last
         n = p.width * p.height * 3
-        mean = np.empty(n, dtype=np.float64)
+        if out is not None:
+            mean = out.reshape(-1)
+            assert mean.dtype == np.float64 and mean.size == n and mean.flags.c_contiguous
+        else:
+            mean = np.empty(n, dtype=np.float64)
         sq = np.empty(n, dtype=np.float64) if want_sumsq else None
         st = Stats()
         self._check(lib().pt_readback(self._h, _dp(mean), _dp(sq) if want_sumsq else None, C.byref(st)), "pt_readback")

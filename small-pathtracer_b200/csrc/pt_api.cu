@@ -1,5 +1,6 @@
 // pt_api.cu — the extern "C" boundary of libptb200.so (include/ptb200.h): context, scene upload,
 // render dispatch, readback, debug entries.  No torch types, plain pointers and sizes.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -394,6 +395,35 @@ int pt_render_into(pt_ctx *ctx, const pt_render_params *p, void *dev_rgb_sum, vo
     return render_common(ctx, p, (double *)dev_rgb_sum, (cudaStream_t)stream);
 }
 
+// per-pixel SUM -> MEAN on the device (the division by `samps` of src/smallpt.cpp:536), so the host only copies
+__global__ void k_scale(const double *__restrict__ in, double *__restrict__ out, size_t n, double scale)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] * scale;
+}
+
+// device -> caller's (pageable) buffer through two pinned staging blocks: the copy of block k+1 over PCIe overlaps the
+// host memcpy of block k
+static int staged_d2h(pt_ctx *ctx, double *dst, const double *d_src, size_t n)
+{
+    const size_t blk = PT_STAGE_ELEMS;
+    const size_t nblk = (n + blk - 1) / blk;
+    auto issue = [&](size_t k) {
+        const size_t off = k * blk, cnt = std::min(blk, n - off);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_stage + (k & 1) * blk, d_src + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_stage[k & 1], ctx->stream);
+        return e;
+    };
+    if (nblk) PT_CUDA(ctx, issue(0));
+    for (size_t k = 0; k < nblk; k++) {
+        if (k + 1 < nblk) PT_CUDA(ctx, issue(k + 1));
+        PT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[k & 1]));
+        const size_t off = k * blk, cnt = std::min(blk, n - off);
+        std::memcpy(dst + off, ctx->h_stage + (k & 1) * blk, cnt * sizeof(double));
+    }
+    return PT_OK;
+}
+
 int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats)
 {
     if (!ctx) return pt_fail(ctx, PT_ERR_ARG, "null context");
@@ -401,25 +431,31 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     const pt_render_params &p = ctx->last;
     const size_t n = (size_t)p.width * p.height * 3;
-    if ((rgb_mean || rgb_sumsq) && ctx->stage_elems < n) {      // pinned staging: D2H at full PCIe rate
-        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-        ctx->h_stage = nullptr; ctx->stage_elems = 0;
-        PT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, n * sizeof(double)));
-        ctx->stage_elems = n;
+    if ((rgb_mean || rgb_sumsq) && !ctx->h_stage) {             // pinned staging: D2H at full PCIe rate
+        PT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, 2 * PT_STAGE_ELEMS * sizeof(double)));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming));
     }
     if (rgb_mean) {
         const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
-        PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const double *hs = ctx->h_stage;
-        if (p.spp > 0) for (size_t i = 0; i < n; i++) rgb_mean[i] = hs[i] / p.spp;
-        else std::memcpy(rgb_mean, hs, n * sizeof(double));
+        if (p.spp > 0) {
+            if (ctx->mean_elems < n) {
+                if (ctx->d_mean) cudaFree(ctx->d_mean);
+                ctx->d_mean = nullptr; ctx->mean_elems = 0;
+                PT_CUDA(ctx, cudaMalloc(&ctx->d_mean, n * sizeof(double)));
+                ctx->mean_elems = n;
+            }
+            k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, 1.0 / p.spp);
+            PT_CUDA(ctx, cudaGetLastError());
+            src = ctx->d_mean;
+        }
+        int rc = staged_d2h(ctx, rgb_mean, src, n);
+        if (rc) return rc;
     }
     if (rgb_sumsq) {
         if (!p.collect_stats) return pt_fail(ctx, PT_ERR_STATE, "sum of squares requested but collect_stats was 0");
-        PT_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, ctx->d_sumsq, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        std::memcpy(rgb_sumsq, ctx->h_stage, n * sizeof(double));
+        int rc = staged_d2h(ctx, rgb_sumsq, ctx->d_sumsq, n);
+        if (rc) return rc;
     }
     if (stats) *stats = ctx->stats;
     return PT_OK;
@@ -514,6 +550,9 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_fixsq) cudaFree(ctx->d_fixsq);
     if (ctx->d_sum) cudaFree(ctx->d_sum);
     if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
+    if (ctx->d_mean) cudaFree(ctx->d_mean);
+    if (ctx->ev_stage[0]) cudaEventDestroy(ctx->ev_stage[0]);
+    if (ctx->ev_stage[1]) cudaEventDestroy(ctx->ev_stage[1]);
     if (ctx->d_objs) cudaFree(ctx->d_objs);
     if (ctx->d_mats) cudaFree(ctx->d_mats);
     if (ctx->d_sphf) cudaFree(ctx->d_sphf);

@@ -24,6 +24,7 @@ struct DevObj64 {
 
 // ------------------------------------------------------------------ context
 struct PtJitKernel;
+#define PT_STAGE_ELEMS ((size_t)1 << 19)   /* 4 MB staging blocks */
 #define PT_JIT_MIN_PATHS (1ull << 25)   /* renders at least this big are worth a ~1 s specialised build (jit_mode 1) */
 
 struct pt_ctx {
@@ -61,8 +62,10 @@ struct pt_ctx {
     unsigned int *h_pinned = nullptr;                  // 2 pinned words for the termination check
     cudaEvent_t ev_batch[2] = {nullptr, nullptr};
     DevStats *h_stats = nullptr;                       // pinned
-    double *h_stage = nullptr;                         // pinned staging for pt_readback
-    size_t stage_elems = 0;
+    double *h_stage = nullptr;                         // pinned staging for pt_readback: two blocks of PT_STAGE_ELEMS
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    double *d_mean = nullptr;                          // per-pixel mean (sum / spp), produced on the device at readback
+    size_t mean_elems = 0;
     DevStats *d_stats = nullptr;
     pt_stats stats{};
     // scene specialisation: 0 = generic kernel only, 1 = specialise renders of >= PT_JIT_MIN_PATHS paths, 2 = always
