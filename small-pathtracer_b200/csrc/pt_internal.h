@@ -24,6 +24,9 @@ struct DevObj64 {
 
 // ------------------------------------------------------------------ context
 struct PtJitKernel;
+#ifndef PT_JIT_SPH_IMM_MAX
+#define PT_JIT_SPH_IMM_MAX 256          /* specialised build: sphere scan tables up to this size become immediates */
+#endif
 #define PT_STAGE_ELEMS ((size_t)1 << 19)   /* 4 MB staging blocks */
 #define PT_JIT_MIN_PATHS (1ull << 25)   /* renders at least this big are worth a ~1 s specialised build (jit_mode 1) */
 

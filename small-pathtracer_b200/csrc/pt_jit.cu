@@ -114,6 +114,14 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
     def_i("code_obj0", S.code_obj0); def_i("light_code", S.light_code);
     def_f("lx0", S.lx0); def_f("lxw", S.lxw); def_f("lz0", S.lz0); def_f("lzw", S.lzw); def_f("ly", S.ly); def_f("larea", S.larea);
     def_f("sph_kM2", S.sph_kM2);
+    if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates
+        std::snprintf(b, sizeof b, "#define PT_J_SPH_IMM %d\nconstexpr float PT_J_SPHF[%d][4] = {\n", PT_JIT_SPH_IMM_MAX, S.n_sph4);
+        h += b;
+        for (int k = 0; k < S.n_sph4; k++) {
+            h += " {"; put_float(h, S.sphf[k].x); h += ","; put_float(h, S.sphf[k].y); h += ","; put_float(h, S.sphf[k].z); h += ","; put_float(h, S.sphf[k].w); h += "},\n";
+        }
+        h += "};\n";
+    }
     h += "constexpr float PT_J_sph_c[3] = {"; put_float(h, S.sph_c[0]); h += ","; put_float(h, S.sph_c[1]); h += ","; put_float(h, S.sph_c[2]); h += "};\n";
     return h;
 }

@@ -1,4 +1,4 @@
 set -x
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s14_n$N.json 2> gpurun_out/bench_s14_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s14_n$N.json
-done
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s15.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu_s15.log
+python tools/abtest.py > gpurun_out/abtest_s15.log 2>&1; cat gpurun_out/abtest_s15.log
