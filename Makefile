@@ -34,10 +34,10 @@ $(OBJDIR)/pt_api.o: $(CSRC)/pt_api.cu $(CSRC)/pt_scene_dev.h $(CSRC)/pt_internal
 $(PKG)/libptb200.so: $(OBJDIR)/pt_validate.o $(OBJDIR)/pt_wavefront.o $(OBJDIR)/pt_api.o $(OBJDIR)/pt_jit.o
 	$(NVCC) $(ARCH) -shared -cudart static $^ -ldl -o $@
 
-$(PKG)/libsmallpt_host.so: $(HOST)/scenes.cpp $(HOST)/host_capi.cpp $(HOST)/smallpt_b200.hpp include/ptb200.h
+$(PKG)/libsmallpt_host.so: $(HOST)/scenes.cpp $(HOST)/host_capi.cpp $(HOST)/smallpt_b200.hpp $(HOST)/scene_io.hpp include/ptb200.h
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Iinclude $(HOST)/scenes.cpp $(HOST)/host_capi.cpp -o $@
 
-$(PKG)/smallpt: $(HOST)/smallpt_main.cpp $(HOST)/scenes.cpp $(HOST)/smallpt_b200.hpp $(PKG)/libptb200.so
+$(PKG)/smallpt: $(HOST)/smallpt_main.cpp $(HOST)/scenes.cpp $(HOST)/smallpt_b200.hpp $(HOST)/scene_io.hpp $(PKG)/libptb200.so
 	$(CXX) -O2 -std=c++17 -Iinclude $(HOST)/smallpt_main.cpp $(HOST)/scenes.cpp -L$(PKG) -lptb200 -Wl,-rpath,'$$ORIGIN' -o $@
 
 oracle:

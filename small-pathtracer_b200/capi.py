@@ -119,6 +119,14 @@ def host_lib():
         L.spt_toInt.argtypes = [C.c_double]
         L.spt_toInt.restype = C.c_int
         L.spt_write_ppm.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.spt_write_ppm_binary.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.spt_write_pfm.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int]
+        L.spt_write_raw64.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.spt_scene_text.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.spt_parse_scene.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.spt_parse_error.restype = C.c_char_p
+        L.spt_parsed_fill.argtypes = [C.POINTER(Sphere), C.POINTER(Plane), C.POINTER(C.c_int), C.POINTER(Light), C.c_int, C.c_int, C.POINTER(Camera)]
+        L.spt_parsed_fill.restype = None
         _host = L
     return _host
 
@@ -184,6 +192,45 @@ def builtin_scene(name, w=512, h=512):
     L.spt_scene_fill(name.encode(), sph, pl, order, C.byref(light))
     sc = Scene(list(sph)[:ns.value], list(pl)[:npl.value], list(order), light, name=name)
     return sc.with_camera(w, h)
+
+
+def scene_text(name):
+    """A built-in scene in the text scene format (host/scene_io.hpp)."""
+    L = host_lib()
+    n = L.spt_scene_text(name.encode(), None, 0)
+    if n < 0:
+        raise PtError(f"unknown scene {name!r}")
+    buf = C.create_string_buffer(n + 1)
+    L.spt_scene_text(name.encode(), buf, n + 1)
+    return buf.value.decode()
+
+
+def parse_scene(text, w=512, h=512):
+    """Text scene format -> Scene (camera from the file's `camera` statement, else the reference's, :521)."""
+    L = host_lib()
+    ns, npl, has_cam = C.c_int(), C.c_int(), C.c_int()
+    n = L.spt_parse_scene(text.encode(), C.byref(ns), C.byref(npl), C.byref(has_cam))
+    if n < 0:
+        raise PtError("scene file: " + L.spt_parse_error().decode())
+    sph = (Sphere * max(1, ns.value))()
+    pl = (Plane * max(1, npl.value))()
+    order = (C.c_int * n)()
+    light, cam = Light(), Camera()
+    L.spt_parsed_fill(sph, pl, order, C.byref(light), w, h, C.byref(cam))
+    return Scene(list(sph)[:ns.value], list(pl)[:npl.value], list(order), light, camera=cam, name="file")
+
+
+def write_image(path, mean, fmt="ppm"):
+    """fmt: 'ppm' (P3, the reference's writer :548-551), 'ppm6' (binary), 'pfm' (float32 linear) or 'raw64'."""
+    a = np.ascontiguousarray(mean, dtype=np.float64)
+    h, w = a.shape[0], a.shape[1]
+    L = host_lib()
+    dp = a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = {"ppm": lambda: L.spt_write_ppm(path.encode(), dp, w, h), "ppm6": lambda: L.spt_write_ppm_binary(path.encode(), dp, w, h),
+          "pfm": lambda: L.spt_write_pfm(path.encode(), dp, w, h),
+          "raw64": lambda: L.spt_write_raw64(path.encode(), dp, w, h, 0, b"mean")}[fmt]()
+    if rc:
+        raise PtError(f"cannot write {path}")
 
 
 def make_camera(lookfrom, lookat, vup, vfov, aspect):

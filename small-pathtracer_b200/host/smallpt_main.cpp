@@ -1,13 +1,14 @@
 // smallpt_main.cpp — the `smallpt` executable: the reference's main() (src/smallpt.cpp:502-557) on the
-// B200 path.  Usage:  smallpt [spp] [--mode nee|cos|uni|nee-cone] [--scene A|B|C|synthetic]
+// B200 path.  Usage:  smallpt [spp] [--mode nee|cos|uni|nee-cone] [--scene A|B|C|synthetic | --scene-file f.scene]
 //                             [--size WxH] [--validate] [--det-sincos] [--seed N] [--out file.ppm]
+//                             [--ppm6 file] [--pfm file] [--raw64 file] [--variance file] [--dump-scene file]
 // `spp` is argv[1] as the north star asks (the reference hard-codes samps = 16 at :508).
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 
-#include "smallpt_b200.hpp"
+#include "scene_io.hpp"
 
 using namespace smallpt_b200;
 
@@ -15,7 +16,7 @@ int main(int argc, char *argv[])
 {
     int w = 512, h = 512;          // :507
     int samps = 16;                // :508
-    std::string mode = "nee", scene_name = "A", out = "image.ppm";
+    std::string mode = "nee", scene_name = "A", out = "image.ppm", scene_file, ppm6, pfm, raw64, variance, dump_scene;
     bool validate = false, det = false;
     uint64_t seed = 0;
     int argi = 1;
@@ -33,6 +34,12 @@ int main(int argc, char *argv[])
         else if (a == "--det-sincos") det = true;
         else if (a == "--seed") seed = std::strtoull(need("--seed"), nullptr, 10);
         else if (a == "--out") out = need("--out");
+        else if (a == "--scene-file") scene_file = need("--scene-file");
+        else if (a == "--ppm6") ppm6 = need("--ppm6");
+        else if (a == "--pfm") pfm = need("--pfm");
+        else if (a == "--raw64") raw64 = need("--raw64");
+        else if (a == "--variance") variance = need("--variance");
+        else if (a == "--dump-scene") dump_scene = need("--dump-scene");
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
     if (samps <= 0 || w <= 0 || h <= 0) { std::cerr << "spp and size must be positive\n"; return 2; }
@@ -42,15 +49,34 @@ int main(int argc, char *argv[])
     p.engine = validate ? PT_ENGINE_FP64_ERAND48 : PT_ENGINE_FP32_PHILOX;
     p.sincos = det ? PT_SINCOS_DET : PT_SINCOS_LIBM;
     p.world = 1;
+    p.collect_stats = variance.empty() ? 0 : 1;
     try {
         auto t1 = std::chrono::high_resolution_clock::now();
-        SceneTable scene = scene_by_name(scene_name);
-        Camera cam(LOOKFROM, Vec(50, 40, 5), Vec(0, 1, 0), 65, float(w) / float(h));   // :521
+        SceneTable scene;
+        CameraSpec cam_spec;                                                           // defaults = the literals of :65,:521
+        if (!scene_file.empty()) {
+            SceneFile sf = load_scene_file(scene_file);
+            scene = sf.table;
+            if (sf.has_camera) cam_spec = sf.camera;
+        } else {
+            scene = scene_by_name(scene_name);
+        }
+        if (!dump_scene.empty()) {
+            std::ofstream o(dump_scene);
+            if (!o) throw std::runtime_error("cannot open " + dump_scene);
+            o << scene_to_text(scene, cam_spec);
+        }
+        Camera cam = cam_spec.make(w, h);                                              // :521
         Renderer r(scene, cam);
         r.render(p);
         pt_stats st{};
-        std::vector<double> c = r.readback(w, h, &st);
+        std::vector<double> sumsq;
+        std::vector<double> c = r.readback(w, h, &st, variance.empty() ? nullptr : &sumsq);
         write_ppm(out, c.data(), w, h);                                                // :548-551
+        if (!ppm6.empty()) write_ppm_binary(ppm6, c.data(), w, h);
+        if (!pfm.empty()) write_pfm(pfm, c.data(), w, h);
+        if (!raw64.empty()) write_raw64(raw64, c.data(), w, h, samps, "mean");
+        if (!variance.empty()) { std::vector<double> var = variance_from(c, sumsq, samps); write_raw64(variance, var.data(), w, h, samps, "variance"); }
         auto t2 = std::chrono::high_resolution_clock::now();
         double rays = double(st.rays_camera + st.rays_scatter + st.rays_shadow);
         std::cout << "PATHS: " << st.paths << "  RAYS: " << (uint64_t)rays << "  MAX DEPTH: " << st.max_depth_seen << std::endl;
