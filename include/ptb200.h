@@ -127,7 +127,13 @@ typedef struct pt_render_params {
     int      max_depth;       /* safety cap on path length; 0 = default (4096) */
     int      queue_capacity;  /* wavefront queue slots; 0 = default (sized to L2) */
     int      collect_stats;   /* 1 = also accumulate per-pixel sum of squares */
-    int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (8) */
+    int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (128) */
+    /* Progressive / checkpointable accumulation (FP32 engine).  accumulate = 1 renders samples
+     * [sample_offset, sample_offset + spp) ON TOP of what the context already holds (same image size, mode, seed and
+     * sharding) instead of starting from zero.  Samples are Philox streams keyed by their index and the accumulators
+     * are integers, so any split of the sample range gives the bit-identical image; pt_readback divides by the total. */
+    int      sample_offset;
+    int      accumulate;
 } pt_render_params;
 
 typedef struct pt_stats {
@@ -183,6 +189,15 @@ int pt_render_into(pt_ctx *ctx, const pt_render_params *params, void *dev_rgb_su
  * toInt (:319-321).  rgb_sumsq (optional, may be NULL) receives per-pixel per-channel sums
  * of squared sample radiance when collect_stats was set.  stats may be NULL. */
 int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats);
+
+/* Resume from a checkpoint: load per-pixel SUMS (and optionally sums of squares) of `spp_done` samples — what
+ * pt_accum_download returned earlier, possibly in another process — into the context's accumulators, so that a
+ * following pt_render with accumulate = 1 and sample_offset = spp_done continues the image.  Values must be the
+ * library's own sums (multiples of 2^-24): they are restored exactly. */
+int pt_accum_upload(pt_ctx *ctx, int width, int height, const double *rgb_sum, const double *rgb_sumsq, int spp_done);
+
+/* Checkpoint: per-pixel SUMS of sample radiance (not means) accumulated so far, and the number of samples in them. */
+int pt_accum_download(pt_ctx *ctx, double *rgb_sum, double *rgb_sumsq, int *spp_done);
 
 /* Device pointer of the context-owned accumulation buffer (w*h*3 doubles: per-pixel SUM of
  * sample radiance) of the last pt_render, for zero-copy gathers. */

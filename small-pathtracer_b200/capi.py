@@ -58,7 +58,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("spp", C.c_int), ("mode", C.c_int),
                 ("engine", C.c_int), ("sincos", C.c_int), ("seed", C.c_uint64),
                 ("tile_rows", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("max_depth", C.c_int),
-                ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("bounces_per_launch", C.c_int)]
+                ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("bounces_per_launch", C.c_int),
+                ("sample_offset", C.c_int), ("accumulate", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -269,11 +270,13 @@ def write_ppm(path, rgb_mean, w, h):
 
 
 def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, sincos=PT_SINCOS_LIBM, seed=0,
-           tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0, bounces_per_launch=0):
+           tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0, bounces_per_launch=0,
+           sample_offset=0, accumulate=0):
     p = RenderParams()
     p.width, p.height, p.spp, p.mode, p.engine, p.sincos, p.seed = w, h, spp, mode, engine, sincos, seed
     p.tile_rows, p.rank, p.world, p.max_depth = tile_rows, rank, world, max_depth
     p.queue_capacity, p.collect_stats, p.bounces_per_launch = queue_capacity, collect_stats, bounces_per_launch
+    p.sample_offset, p.accumulate = sample_offset, accumulate
     return p
 
 
@@ -282,7 +285,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
-           "pt_set_specialisation", "pt_debug_specialise", "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_debug_specialise", "pt_accum_upload", "pt_accum_download", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -297,6 +300,8 @@ def lib():
         L.pt_render.argtypes = [vp, C.POINTER(RenderParams)]
         L.pt_render_into.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
         L.pt_readback.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(Stats)]
+        L.pt_accum_upload.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        L.pt_accum_download.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.pt_accum_device_ptr.argtypes = [vp]
         L.pt_accum_device_ptr.restype = vp
         L.pt_debug_intersect.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
@@ -384,6 +389,25 @@ class Context:
         if want_sumsq:
             return mean, sq.reshape(p.height, p.width, 3), st
         return mean, st
+
+    def accum_download(self, want_sumsq=False):
+        """Checkpoint: (per-pixel sums (H, W, 3), sums of squares | None, samples per pixel in them)."""
+        p = self.last
+        n = p.width * p.height * 3
+        s = np.empty(n, dtype=np.float64)
+        sq = np.empty(n, dtype=np.float64) if want_sumsq else None
+        done = C.c_int(0)
+        self._check(lib().pt_accum_download(self._h, _dp(s), _dp(sq) if want_sumsq else None, C.byref(done)), "pt_accum_download")
+        shape = (p.height, p.width, 3)
+        return s.reshape(shape), (sq.reshape(shape) if want_sumsq else None), done.value
+
+    def accum_upload(self, sums, spp_done, sumsq=None):
+        """Resume: load a checkpoint; follow with render(params(..., sample_offset=spp_done, accumulate=1))."""
+        a = np.ascontiguousarray(sums, dtype=np.float64)
+        h, w = a.shape[0], a.shape[1]
+        q = np.ascontiguousarray(sumsq, dtype=np.float64) if sumsq is not None else None
+        self._check(lib().pt_accum_upload(self._h, w, h, _dp(a), _dp(q) if q is not None else None, spp_done), "pt_accum_upload")
+        self.last = params(w, h, spp_done)
 
     def stats(self):
         st = Stats()

@@ -289,6 +289,9 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (!ctx || !p) return pt_fail(ctx, PT_ERR_ARG, "null argument");
     if (p->width <= 0 || p->height <= 0 || p->spp < 0 || p->width > 65535 || p->height > 65535)
         return pt_fail(ctx, PT_ERR_ARG, "width/height must be in 1..65535 and spp >= 0");
+    if (p->sample_offset < 0) return pt_fail(ctx, PT_ERR_ARG, "sample_offset must be >= 0");
+    if (p->accumulate && p->engine != PT_ENGINE_FP32_PHILOX)
+        return pt_fail(ctx, PT_ERR_ARG, "accumulate = 1 is an FP32 engine feature (the erand48 replay consumes one sequential stream per row)");
     if (p->mode < PT_MODE_NEE_REF_RECT || p->mode > PT_MODE_NEE_CONE_SPHERE) return pt_fail(ctx, PT_ERR_ARG, "bad mode");
     if (p->engine != PT_ENGINE_FP32_PHILOX && p->engine != PT_ENGINE_FP64_ERAND48) return pt_fail(ctx, PT_ERR_ARG, "bad engine");
     const int world = p->world > 0 ? p->world : 1;
@@ -312,6 +315,8 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (p->collect_stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_sumsq, 0, n_acc * sizeof(double), s));
     PT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), s));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    if (p->accumulate && (!ctx->rendered_fp32 || ctx->accum_spp <= 0 || ctx->last.width != p->width || ctx->last.height != p->height))
+        return pt_fail(ctx, PT_ERR_STATE, "accumulate = 1 needs a previous FP32 render (or pt_accum_upload) of the same image size");
     ctx->last = *p;
     ctx->rendered = false;
     ctx->jit = nullptr;
@@ -347,6 +352,8 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
         st.rays_scatter = ds.rays_scatter;
     }
     ctx->rendered = true;
+    ctx->rendered_fp32 = p->engine == PT_ENGINE_FP32_PHILOX;
+    if (!ctx->rendered_fp32) ctx->accum_spp = p->spp;
     return PT_OK;
 }
 
@@ -445,7 +452,7 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
                 PT_CUDA(ctx, cudaMalloc(&ctx->d_mean, n * sizeof(double)));
                 ctx->mean_elems = n;
             }
-            k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, 1.0 / p.spp);
+            k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, 1.0 / (double)(ctx->accum_spp > 0 ? ctx->accum_spp : p.spp));
             PT_CUDA(ctx, cudaGetLastError());
             src = ctx->d_mean;
         }
@@ -458,6 +465,72 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
         if (rc) return rc;
     }
     if (stats) *stats = ctx->stats;
+    return PT_OK;
+}
+
+// exact double <-> 2^-24 fixed point (the library's own sums are multiples of 2^-24 below 2^40)
+__global__ void k_to_fix(const double *__restrict__ in, unsigned long long *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned long long)__double2ull_rn(in[i] * 16777216.0);
+}
+
+int pt_accum_upload(pt_ctx *ctx, int width, int height, const double *rgb_sum, const double *rgb_sumsq, int spp_done)
+{
+    if (!ctx || !rgb_sum || width <= 0 || height <= 0 || spp_done <= 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height * 3;
+    if (ctx->fix_elems < n) {
+        if (ctx->d_fix) cudaFree(ctx->d_fix);
+        if (ctx->d_fixsq) cudaFree(ctx->d_fixsq);
+        ctx->d_fix = ctx->d_fixsq = nullptr; ctx->fix_elems = 0;
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_fix, n * sizeof(unsigned long long)));
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_fixsq, n * sizeof(unsigned long long)));
+        ctx->fix_elems = n;
+    }
+    if (ctx->accum_elems < n) {
+        if (ctx->d_sum) cudaFree(ctx->d_sum);
+        if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
+        ctx->d_sum = ctx->d_sumsq = nullptr; ctx->accum_elems = 0;
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_sum, n * sizeof(double)));
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_sumsq, n * sizeof(double)));
+        ctx->accum_elems = n;
+    }
+    PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sum, rgb_sum, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_to_fix<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_sum, ctx->d_fix, n);
+    if (rgb_sumsq) {
+        PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_sumsq, rgb_sumsq, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        k_to_fix<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_sumsq, ctx->d_fixsq, n);
+    }
+    PT_CUDA(ctx, cudaGetLastError());
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->fix_has_sq = rgb_sumsq != nullptr;
+    ctx->accum_spp = spp_done;
+    ctx->d_sum_ext = nullptr;
+    std::memset(&ctx->last, 0, sizeof ctx->last);
+    ctx->last.width = width; ctx->last.height = height; ctx->last.spp = spp_done; ctx->last.world = 1;
+    ctx->last.collect_stats = rgb_sumsq ? 1 : 0;
+    ctx->rendered = true;
+    ctx->rendered_fp32 = true;
+    return PT_OK;
+}
+
+int pt_accum_download(pt_ctx *ctx, double *rgb_sum, double *rgb_sumsq, int *spp_done)
+{
+    if (!ctx) return pt_fail(ctx, PT_ERR_ARG, "null context");
+    if (!ctx->rendered) return pt_fail(ctx, PT_ERR_STATE, "pt_accum_download before a successful pt_render");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->last.width * ctx->last.height * 3;
+    if (rgb_sum) {
+        const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
+        PT_CUDA(ctx, cudaMemcpyAsync(rgb_sum, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (rgb_sumsq) {
+        if (!ctx->last.collect_stats) return pt_fail(ctx, PT_ERR_STATE, "sum of squares requested but collect_stats was 0");
+        PT_CUDA(ctx, cudaMemcpyAsync(rgb_sumsq, ctx->d_sumsq, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (spp_done) *spp_done = (int)ctx->accum_spp;
     return PT_OK;
 }
 

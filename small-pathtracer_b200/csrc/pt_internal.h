@@ -50,11 +50,14 @@ struct pt_ctx {
     // render state
     pt_render_params last{};
     bool rendered = false;
+    bool rendered_fp32 = false;                        // the accumulators hold an FP32-engine image (accumulate = 1 may follow)
     double *d_sum = nullptr, *d_sumsq = nullptr;       // context-owned accumulation (w*h*3)
     double *d_sum_ext = nullptr;                       // caller-owned target of pt_render_into
     size_t accum_elems = 0;
     unsigned long long *d_fix = nullptr, *d_fixsq = nullptr;  // FP32 engine fixed-point accumulators
     size_t fix_elems = 0;
+    long long accum_spp = 0;                           // samples per pixel held by the accumulators (progressive renders add up)
+    bool fix_has_sq = false;                           // d_fixsq holds the sums of squares of those samples
     // wavefront queues (FP32 engine)
     float4 *q[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     int q_capacity = 0;

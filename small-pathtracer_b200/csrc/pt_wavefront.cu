@@ -155,8 +155,17 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         PT_CUDA(ctx, cudaMalloc(&ctx->d_fixsq, n_acc * sizeof(unsigned long long)));
         ctx->fix_elems = n_acc;
     }
-    PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fix, 0, n_acc * sizeof(unsigned long long), s));
-    if (stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fixsq, 0, n_acc * sizeof(unsigned long long), s));
+    const bool accumulate = p->accumulate != 0;
+    if (accumulate) {       // render_common checked that the accumulators hold an FP32 image of this size
+        if (stats && !ctx->fix_has_sq) return pt_fail(ctx, PT_ERR_STATE, "collect_stats = 1 cannot be added to accumulators without sums of squares");
+    } else {
+        PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fix, 0, n_acc * sizeof(unsigned long long), s));
+        if (stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_fixsq, 0, n_acc * sizeof(unsigned long long), s));
+        ctx->accum_spp = 0;
+        ctx->fix_has_sq = stats;
+    }
+    if (!stats) ctx->fix_has_sq = false;
+    ctx->accum_spp += p->spp;
 
     int it_total = 0;
     if (owned_pixels > 0 && p->spp > 0) {
@@ -235,6 +244,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.cam_h[0] = (float)c.horizontal.x; P.cam_h[1] = (float)c.horizontal.y; P.cam_h[2] = (float)c.horizontal.z;
         P.cam_v[0] = (float)c.vertical.x; P.cam_v[1] = (float)c.vertical.y; P.cam_v[2] = (float)c.vertical.z;
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
+        P.smp0 = (unsigned int)p->sample_offset;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
         P.seed_jitter = (P.seed_lo ^ (P.seed_hi * 0x85EBCA6Bu)) + 0xC2B2AE35u;
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;

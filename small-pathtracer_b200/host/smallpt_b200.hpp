@@ -235,6 +235,17 @@ public:
         check(pt_readback(ctx_, rgb.data(), sumsq ? sumsq->data() : nullptr, stats), "pt_readback");
         return rgb;
     }
+    // checkpoint / resume of the accumulators (per-pixel SUMS and the number of samples in them)
+    std::vector<double> accum_download(int w, int h, int *spp_done)
+    {
+        std::vector<double> sums(size_t(w) * h * 3);
+        check(pt_accum_download(ctx_, sums.data(), nullptr, spp_done), "pt_accum_download");
+        return sums;
+    }
+    void accum_upload(int w, int h, const std::vector<double> &sums, int spp_done)
+    {
+        check(pt_accum_upload(ctx_, w, h, sums.data(), nullptr, spp_done), "pt_accum_upload");
+    }
     pt_ctx *ctx() { return ctx_; }
 private:
     void check(int rc, const char *what)

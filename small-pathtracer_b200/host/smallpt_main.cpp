@@ -2,7 +2,9 @@
 // B200 path.  Usage:  smallpt [spp] [--mode nee|cos|uni|nee-cone] [--scene A|B|C|synthetic | --scene-file f.scene]
 //                             [--size WxH] [--validate] [--det-sincos] [--seed N] [--out file.ppm]
 //                             [--ppm6 file] [--pfm file] [--raw64 file] [--variance file] [--dump-scene file]
+//                             [--chunk N] [--checkpoint file] [--resume file]      progressive accumulation
 // `spp` is argv[1] as the north star asks (the reference hard-codes samps = 16 at :508).
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -16,7 +18,8 @@ int main(int argc, char *argv[])
 {
     int w = 512, h = 512;          // :507
     int samps = 16;                // :508
-    std::string mode = "nee", scene_name = "A", out = "image.ppm", scene_file, ppm6, pfm, raw64, variance, dump_scene;
+    std::string mode = "nee", scene_name = "A", out = "image.ppm", scene_file, ppm6, pfm, raw64, variance, dump_scene, checkpoint, resume;
+    int chunk = 0;
     bool validate = false, det = false;
     uint64_t seed = 0;
     int argi = 1;
@@ -40,6 +43,9 @@ int main(int argc, char *argv[])
         else if (a == "--raw64") raw64 = need("--raw64");
         else if (a == "--variance") variance = need("--variance");
         else if (a == "--dump-scene") dump_scene = need("--dump-scene");
+        else if (a == "--chunk") chunk = std::atoi(need("--chunk"));
+        else if (a == "--checkpoint") checkpoint = need("--checkpoint");
+        else if (a == "--resume") resume = need("--resume");
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
     }
     if (samps <= 0 || w <= 0 || h <= 0) { std::cerr << "spp and size must be positive\n"; return 2; }
@@ -68,10 +74,42 @@ int main(int argc, char *argv[])
         }
         Camera cam = cam_spec.make(w, h);                                              // :521
         Renderer r(scene, cam);
-        r.render(p);
+        // Progressive accumulation: the sample range [0, samps) in chunks; every chunk continues the same image (samples are
+        // Philox streams keyed by their index), a checkpoint holds the per-pixel sums and the number of samples in them.
+        if ((chunk > 0 || !resume.empty() || !checkpoint.empty()) && (validate || !variance.empty())) {
+            std::cerr << "--chunk/--checkpoint/--resume apply to the FP32 engine without --variance\n";
+            return 2;
+        }
+        int done = 0;
+        double render_ms = 0;
+        uint64_t paths = 0, rays_c = 0, rays_s = 0, rays_sh = 0;
+        if (!resume.empty()) {
+            int cw = 0, ch = 0, cspp = 0;
+            std::string what;
+            std::vector<double> sums = read_raw64(resume, cw, ch, cspp, what);
+            if (cw != w || ch != h || what != "sum" || cspp <= 0) throw std::runtime_error(resume + ": not a checkpoint of a " + std::to_string(w) + "x" + std::to_string(h) + " image");
+            r.accum_upload(w, h, sums, cspp);
+            done = cspp;
+        }
         pt_stats st{};
+        if (done >= samps && done > 0) { p.spp = 0; }
+        while (done < samps) {
+            const int n = chunk > 0 ? std::min(chunk, samps - done) : samps - done;
+            p.spp = n; p.sample_offset = done; p.accumulate = done > 0 ? 1 : 0;
+            r.render(p);
+            done += n;
+            pt_stats cs{};
+            pt_readback(r.ctx(), nullptr, nullptr, &cs);
+            render_ms += cs.render_ms; paths += cs.paths; rays_c += cs.rays_camera; rays_s += cs.rays_scatter; rays_sh += cs.rays_shadow;
+            if (!checkpoint.empty()) {
+                int spp_done = 0;
+                std::vector<double> sums = r.accum_download(w, h, &spp_done);
+                write_raw64(checkpoint, sums.data(), w, h, spp_done, "sum");
+            }
+        }
         std::vector<double> sumsq;
         std::vector<double> c = r.readback(w, h, &st, variance.empty() ? nullptr : &sumsq);
+        if (render_ms > 0) { st.render_ms = render_ms; st.paths = paths; st.rays_camera = rays_c; st.rays_scatter = rays_s; st.rays_shadow = rays_sh; }
         write_ppm(out, c.data(), w, h);                                                // :548-551
         if (!ppm6.empty()) write_ppm_binary(ppm6, c.data(), w, h);
         if (!pfm.empty()) write_pfm(pfm, c.data(), w, h);

@@ -180,3 +180,30 @@ def test_scene_specialised_kernel_matches_the_generic_one(scene, mode):
     same = np.isclose(m0, m1, rtol=1e-5, atol=1e-7).all(axis=2)
     assert same.mean() > 0.97, f"only {100 * same.mean():.2f} % of pixels agree"
     assert abs(m0.mean() - m1.mean()) < 2e-3 * m0.mean()
+
+
+def test_progressive_accumulation_and_checkpoint_resume_are_bit_identical():
+    # samples are Philox streams keyed by their index and the accumulators are integers: any split of the sample range,
+    # with or without a trip of the sums through host memory (checkpoint / resume), gives the one-shot image
+    w, h, spp = 128, 96, 48
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(w, h, spp, mode=0, seed=3))
+        one_shot, _ = c.readback()
+        for k, (off, n) in enumerate(((0, 16), (16, 8), (24, 24))):
+            c.render(ptb.params(w, h, n, mode=0, seed=3, sample_offset=off, accumulate=1 if k else 0))
+        chunked, _ = c.readback()
+        assert np.array_equal(chunked, one_shot)
+        c.render(ptb.params(w, h, 20, mode=0, seed=3))
+        sums, _, done = c.accum_download()
+        assert done == 20
+    with ptb.Context(sc) as c2:                      # "another process": a fresh context resumes from the checkpoint
+        c2.accum_upload(sums, done)
+        c2.render(ptb.params(w, h, spp - done, mode=0, seed=3, sample_offset=done, accumulate=1))
+        resumed, _ = c2.readback()
+        assert np.array_equal(resumed, one_shot)
+        with pytest.raises(ptb.PtError, match="accumulate"):
+            c2.render(ptb.params(w, h, 4, mode=0, engine=ptb.PT_ENGINE_FP64_ERAND48, accumulate=1))
+    with ptb.Context(sc) as c3:
+        with pytest.raises(ptb.PtError, match="accumulate = 1 needs"):
+            c3.render(ptb.params(w, h, 4, mode=0, accumulate=1))

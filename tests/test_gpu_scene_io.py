@@ -46,3 +46,17 @@ def test_smallpt_executable_outputs(tmp_path):
     pfm = open(out["pfm"], "rb").read()
     data = np.frombuffer(pfm[len(b"PF\n64 48\n-1.0\n"):], dtype="<f4").reshape(48, 64, 3)[::-1]
     assert np.allclose(data.reshape(-1), mean.astype(np.float32))
+
+
+def test_smallpt_executable_chunked_checkpoint_resume(tmp_path):
+    exe = os.path.join(ROOT, "small-pathtracer_b200", "smallpt")
+    a, b, ck = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm"), str(tmp_path / "ck.f64")
+    base = [exe, "--scene", "A", "--size", "64x48", "--seed", "9"]
+    assert subprocess.run([exe, "24"] + base[1:] + ["--out", a], capture_output=True).returncode == 0
+    # 10 samples in chunks of 4 with a checkpoint, then resume up to 24
+    r = subprocess.run([exe, "10"] + base[1:] + ["--chunk", "4", "--checkpoint", ck, "--out", b], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(ck, "rb").readline().split()[:5] == [b"PTB200F64", b"64", b"48", b"3", b"10"]
+    r = subprocess.run([exe, "24"] + base[1:] + ["--resume", ck, "--chunk", "5", "--out", b], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(a).read() == open(b).read()

@@ -1,4 +1,3 @@
 set -x
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s15.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/pytest_gpu_s15.log
-python tools/abtest.py > gpurun_out/abtest_s15.log 2>&1; cat gpurun_out/abtest_s15.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s16.log 2>&1; echo "pytest rc=$?"
+tail -25 gpurun_out/pytest_gpu_s16.log
