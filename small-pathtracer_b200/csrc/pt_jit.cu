@@ -141,8 +141,17 @@ int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::strin
         if (FILE *f = std::fopen(keep, "w")) { std::fwrite(src.data(), 1, src.size(), f); std::fclose(f); }
     }
     if (n.CreateProgram(&prog, src.c_str(), name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return PT_ERR_STATE; }
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
-    const nvrtcResult rc = n.CompileProgram(prog, 4, opts);
+    std::vector<std::string> extra;                       // PTB200_JIT_OPTS: extra NVRTC options (tuning experiments)
+    if (const char *e = std::getenv("PTB200_JIT_OPTS")) {
+        std::string cur;
+        for (const char *q = e;; q++) {
+            if (*q == ' ' || *q == 0) { if (!cur.empty()) extra.push_back(cur); cur.clear(); if (!*q) break; }
+            else cur += *q;
+        }
+    }
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    for (const std::string &x : extra) opts.push_back(x.c_str());
+    const nvrtcResult rc = n.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t ls = 0;
     n.GetProgramLogSize(prog, &ls);
     if (ls > 1) { log.resize(ls); n.GetProgramLog(prog, &log[0]); }

@@ -1,3 +1,2 @@
 set -x
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s16.log 2>&1; echo "pytest rc=$?"
-tail -25 gpurun_out/pytest_gpu_s16.log
+python tools/sweep_jit_opts.py > gpurun_out/sweep_jit_opts_s17.log 2>&1; cat gpurun_out/sweep_jit_opts_s17.log
