@@ -213,6 +213,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         KParams P{};
         P.gen_counter = (unsigned long long *)ctx->d_counts;
         P.warp_chunk = ctx->d_warp_chunk;
+        P.capacity = (unsigned int)cap;
         P.iters = p->bounces_per_launch > 0 ? p->bounces_per_launch : PT_DEFAULT_ITERS;
         P.iters_tail = P.iters < PT_DEFAULT_ITERS_TAIL ? P.iters : PT_DEFAULT_ITERS_TAIL;
         P.iters_drain = p->bounces_per_launch > 0 ? P.iters : PT_DEFAULT_ITERS_DRAIN;
@@ -264,6 +265,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
                 if (it >= max_it) { rc2 = pt_fail(ctx, PT_ERR_STATE, "wavefront iteration limit reached"); break; }
                 for (int a = 0; a < 4; a++) { P.qin[a] = ctx->q[it & 1][a]; P.qout[a] = ctx->q[(it + 1) & 1][a]; }
                 P.n_in = n_it + it; P.n_out = n_it + it + 1;
+                P.first_launch = it == 0 ? 1 : 0;
                 switch (p->mode) {
                 case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, blocks, s, P, jk); break;
                 case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, blocks, s, P, jk); break;

@@ -207,3 +207,23 @@ def test_progressive_accumulation_and_checkpoint_resume_are_bit_identical():
     with ptb.Context(sc) as c3:
         with pytest.raises(ptb.PtError, match="accumulate = 1 needs"):
             c3.render(ptb.params(w, h, 4, mode=0, accumulate=1))
+
+
+def test_small_renders_that_exhaust_generation_inside_the_first_launch():
+    # regression: with few samples the path indices run out while the FIRST launch is still starting blocks; the
+    # "nothing left" decisions must be uniform per block / per warp (they steer barriers and warp-synchronous code).
+    # The image must not depend on how many slots are in flight, so a tiny queue (different schedule) is the reference.
+    w = h = 512
+    for scene, mode in (("A", 1), ("B", 1), ("A", 0)):
+        sc = ptb.builtin_scene(scene, w, h)
+        with ptb.Context(sc) as c:
+            for spec in (2, 0):
+                c.set_specialisation(spec)
+                for spp in (1, 2, 3, 5, 16):
+                    for _ in range(2):
+                        c.render(ptb.params(w, h, spp, mode=mode, seed=spp))
+                        full, st = c.readback()
+                        assert st.paths == w * h * spp
+                    c.render(ptb.params(w, h, spp, mode=mode, seed=spp, queue_capacity=8192, bounces_per_launch=3))
+                    small, _ = c.readback()
+                    assert np.array_equal(full, small), (scene, mode, spec, spp)
