@@ -122,6 +122,15 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
         }
         h += "};\n";
     }
+    if (S.n_huge > 0 && S.n_huge <= 16) {          // the huge-sphere table (FP64) as literals
+        std::snprintf(b, sizeof b, "#define PT_J_HUGE_IMM 1\nconstexpr double PT_J_HUGE[%d][4] = {\n", S.n_huge);
+        h += b;
+        for (int k = 0; k < S.n_huge; k++) {
+            std::snprintf(b, sizeof b, " {%a, %a, %a, %a},\n", S.huge[k][0], S.huge[k][1], S.huge[k][2], S.huge[k][3]);
+            h += b;
+        }
+        h += "};\n";
+    }
     h += "constexpr float PT_J_sph_c[3] = {"; put_float(h, S.sph_c[0]); h += ","; put_float(h, S.sph_c[1]); h += ","; put_float(h, S.sph_c[2]); h += "};\n";
     return h;
 }
