@@ -232,6 +232,10 @@ int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
  * environment variable PTB200_JIT overrides the default), 2 = always.  pt_stats.specialised reports what ran. */
 int pt_set_specialisation(pt_ctx *ctx, int mode);
 
+/* The context's statistics record as it stands (pt_readback needs a finished render; the debug entries only set
+ * `specialised`). Test entry. */
+int pt_debug_stats(pt_ctx *ctx, pt_stats *stats);
+
 /* Host-only (no device needed): the specialisation header generated for `scene` and render mode `mode`, and the
  * size of the sm_100a cubin NVRTC builds from it.  spec_out/cubin_bytes/seconds may be NULL. Test entry. */
 int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t spec_cap, size_t *cubin_bytes,

@@ -285,7 +285,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
-           "pt_set_specialisation", "pt_debug_specialise", "pt_accum_upload", "pt_accum_download", "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -310,6 +310,7 @@ def lib():
         L.pt_debug_philox2x32.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
         L.pt_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pt_set_specialisation.argtypes = [vp, C.c_int]
+        L.pt_debug_stats.argtypes = [vp, C.POINTER(Stats)]
         L.pt_debug_specialise.argtypes = [C.POINTER(SceneDesc), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
         L.pt_destroy.argtypes = [vp]
         L.pt_destroy.restype = None
@@ -389,6 +390,12 @@ class Context:
         if want_sumsq:
             return mean, sq.reshape(p.height, p.width, 3), st
         return mean, st
+
+    def stats_raw(self):
+        """pt_stats without requiring a finished render (debug entries update `specialised`)."""
+        st = Stats()
+        lib().pt_debug_stats(self._h, C.byref(st))
+        return st
 
     def accum_download(self, want_sumsq=False):
         """Checkpoint: (per-pixel sums (H, W, 3), sums of squares | None, samples per pixel in them)."""

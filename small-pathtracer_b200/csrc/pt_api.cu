@@ -359,6 +359,13 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
 
 int pt_render(pt_ctx *ctx, const pt_render_params *p) { return render_common(ctx, p, nullptr, nullptr); }
 
+int pt_debug_stats(pt_ctx *ctx, pt_stats *stats)
+{
+    if (!ctx || !stats) return PT_ERR_ARG;
+    *stats = ctx->stats;
+    return PT_OK;
+}
+
 int pt_set_specialisation(pt_ctx *ctx, int mode)
 {
     if (!ctx || mode < 0 || mode > 2) return pt_fail(ctx, PT_ERR_ARG, "specialisation mode must be 0, 1 or 2");

@@ -87,11 +87,12 @@ int pt_fail(pt_ctx *ctx, int code, const std::string &msg);
 struct PtJitKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kern = nullptr;
+    cudaKernel_t kern_isect = nullptr;     // k_intersect_jit (pt_debug_intersect through the specialised closest_hit)
     double compile_seconds = 0;
 };
-std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats);
+std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false);
 int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
-PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats);
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false);
 #define PT_CUDA(ctx, call)                                                                      \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \

@@ -78,12 +78,13 @@ std::map<std::string, PtJitKernel *> g_cache;       // key = specialisation head
 }  // namespace
 
 // The specialisation header of a scene: everything k_bounce reads through PT_SC / PT_J_SLOT.
-std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
+std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect)
 {
     std::string h;
     char b[256];
     std::snprintf(b, sizeof b, "#define PT_JIT 1\n#define PT_J_MODE %d\n#define PT_J_STATS %d\n", mode, stats ? 1 : 0);
     h += b;
+    if (with_intersect) h += "#define PT_J_WITH_INTERSECT 1\n";    // also build k_intersect_jit (pt_debug_intersect)
     std::snprintf(b, sizeof b, "constexpr int PT_J_NSLOT[3] = {%d, %d, %d};\n#define PT_J_NOVF %d\n", S.n_slot[0], S.n_slot[1], S.n_slot[2], S.ovf_begin[3]);
     h += b;
     h += "constexpr float PT_J_SLOT[3][16][3] = {\n";         // k, a1, b1
@@ -119,6 +120,19 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats)
         h += b;
         for (int k = 0; k < S.n_sph4; k++) {
             h += " {"; put_float(h, S.sphf[k].x); h += ","; put_float(h, S.sphf[k].y); h += ","; put_float(h, S.sphf[k].z); h += ","; put_float(h, S.sphf[k].w); h += "},\n";
+        }
+        h += "};\n";
+    }
+    if (S.n_tilt > 0 && S.n_tilt <= 16) {          // tilted planes: {n, n.p0} {s, s.p0} {t, t.p0} {hs, ht, -, -} as literals
+        std::snprintf(b, sizeof b, "#define PT_J_TILT_IMM 1\nconstexpr float PT_J_TILT[%d][16] = {\n", S.n_tilt);
+        h += b;
+        for (int k = 0; k < S.n_tilt; k++) {
+            h += " {";
+            for (int r = 0; r < 4; r++) {
+                const float4 v = S.tilt[k][r];
+                put_float(h, v.x); h += ","; put_float(h, v.y); h += ","; put_float(h, v.z); h += ","; put_float(h, v.w); h += ",";
+            }
+            h += "},\n";
         }
         h += "};\n";
     }
@@ -178,10 +192,10 @@ int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::strin
 }
 
 // The specialised kernel for the context's current scene, or nullptr (generic kernel) when JIT is off/unavailable.
-PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats)
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
 {
     if (!ctx->fp32_ok) return nullptr;
-    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats);
+    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats, with_intersect);
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(spec);
     if (it != g_cache.end()) return it->second;          // may be nullptr: a failed build is not retried
@@ -194,6 +208,7 @@ PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats)
         jk->compile_seconds = secs;
         cudaError_t e = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
         if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk->kern, jk->lib, "k_bounce_jit");
+        if (e == cudaSuccess && with_intersect && cudaLibraryGetKernel(&jk->kern_isect, jk->lib, "k_intersect_jit") != cudaSuccess) { jk->kern_isect = nullptr; cudaGetLastError(); }
         if (e != cudaSuccess) {
             log = std::string("loading the specialised module: ") + cudaGetErrorString(e);
             cudaGetLastError();

@@ -43,31 +43,6 @@ __global__ void k_resolve(const unsigned long long *__restrict__ fix, const unsi
     if (sumsq && fixsq) sumsq[i] = (double)fixsq[i] * PT_FIX_INV;
 }
 
-// pt_debug_intersect, precision 32
-__global__ void k_intersect_fp32(const double *__restrict__ rays, int n_rays, double *__restrict__ t_out, int *__restrict__ id_out,
-                                 const MatF32 *__restrict__ mats, const float4 *__restrict__ sphf)
-{
-    __shared__ float4 s_sphf[2 * (PT_MAX_OBJ + 4)];
-    for (int k = threadIdx.x; k < c_scene.n_sph4; k += blockDim.x) { s_sphf[k] = sphf[k]; s_sphf[PT_MAX_OBJ + 4 + k] = sphf[PT_MAX_OBJ + 4 + k]; }
-    __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rays) return;
-    const double *r = rays + (size_t)i * 6;
-    F3 o = f3((float)r[0], (float)r[1], (float)r[2]), d = f3((float)r[3], (float)r[4], (float)r[5]);
-    float t; int code;
-    closest_hit(o, d, -1, s_sphf, t, code);
-    int id = -1;
-    if (code >= 0) {
-        // report the t the shading stage uses (refined once for the winning object) and the scene id
-        const MatF32 m = mats[code];
-        F3 x;
-        refine_hit(o, d, t, __float_as_int(m.e_type.w), m.geom, m.aux, x);
-        id = __float_as_int(m.aux.w);
-    }
-    t_out[i] = id >= 0 ? (double)t : 1e20;
-    id_out[i] = id;
-}
-
 __global__ void k_philox2(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,6 +283,22 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int *d_id, cudaStream_t s)
 {
     if (!ctx->fp32_ok) return pt_fail(ctx, PT_ERR_ARG, "scene does not fit the FP32 engine: " + ctx->fp32_why);
+    if (ctx->jit_mode >= 2) {       // specialisation forced: answer with the closest_hit of the scene-specialised build
+        const PtJitKernel *jk = pt_jit_get(ctx, PT_MODE_COS, false, true);
+        void *dptr = nullptr;
+        size_t bytes = 0;
+        if (jk && jk->kern_isect && cudaLibraryGetGlobal(&dptr, &bytes, jk->lib, "c_scene") == cudaSuccess && bytes == sizeof(SceneF32)) {
+            PT_CUDA(ctx, cudaMemcpyAsync(dptr, ctx->h_scene32, sizeof(SceneF32), cudaMemcpyHostToDevice, s));
+            const MatF32 *mats = ctx->d_mats;
+            const float4 *sphf = ctx->d_sphf;
+            void *args[] = {(void *)&d_rays, (void *)&n, (void *)&d_t, (void *)&d_id, (void *)&mats, (void *)&sphf};
+            PT_CUDA(ctx, cudaLaunchKernel((const void *)jk->kern_isect, dim3((n + 127) / 128), dim3(128), args, 0, s));
+            ctx->stats.specialised = 1;
+            return PT_OK;
+        }
+        cudaGetLastError();
+    }
+    ctx->stats.specialised = 0;
     PT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_scene, ctx->h_scene32, sizeof(SceneF32), 0, cudaMemcpyHostToDevice, s));
     k_intersect_fp32<<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats, ctx->d_sphf);
     PT_CUDA(ctx, cudaGetLastError());

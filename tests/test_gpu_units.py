@@ -95,8 +95,9 @@ def _hit_geometry(sc, rays, t_o, id_o):
     return near, cosi
 
 
+@pytest.mark.parametrize("spec", [0, 2], ids=["generic", "specialised"])
 @pytest.mark.parametrize("scene", ["A", "B", "C", "synthetic"])
-def test_fp32_intersect_same_id_and_t_within_1e6(scene):
+def test_fp32_intersect_same_id_and_t_within_1e6(scene, spec):
     """north-star gate: identical hit id and t within 1e-6 relative.  Rays are FP32-exact so both sides see the
     same inputs.  What FP32 (24-bit significands, coordinates up to ~170) can promise is an ABSOLUTE position
     accuracy of ~1e-5, i.e. |dt| <= 1e-6 * max(t, S) with S = 200 the scene extent, for rays that are not
@@ -110,7 +111,9 @@ def test_fp32_intersect_same_id_and_t_within_1e6(scene):
     rays = room_rays(400000, 12, f32_exact=True, margin=4.0)
     t_o, id_o = ptb.oracle_intersect(sc, rays)
     with ptb.Context(sc) as c:
+        c.set_specialisation(spec)      # 2: closest_hit of the NVRTC build (scene constants as immediates)
         t, ids = c.intersect(rays, 32)
+        assert c.stats_raw().specialised == (1 if spec else 0)
     same = ids == id_o
     assert same.mean() > 0.9995, f"id mismatches: {(~same).sum()}"
     assert np.all(t[ids < 0] == 1e20)

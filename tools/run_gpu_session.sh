@@ -1,2 +1,1 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s22.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_s22.log
-python tools/abtest.py > gpurun_out/abtest_s22.log 2>&1; cat gpurun_out/abtest_s22.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s24.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu_s24.log
