@@ -46,6 +46,17 @@ def read_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
+def traffic_per_launch(workload, launches_per_step):
+    """DRAM bytes per k_bounce launch from the committed ncu --set full capture of this workload (profiles/r01_traffic.json):
+    whole-step dram__bytes_read + dram__bytes_write divided by the launches of a step, like `avg_launch_ms`."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_per_step"] / max(1, launches_per_step)
+    except Exception:                   # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region, sampled in-process through NVML every ~5 ms
     (nvidia-smi -lms cannot resolve a region that lasts tens of milliseconds)."""
@@ -362,7 +373,7 @@ def main():
                 "peak_theoretical": fp32_theory, "frac_of_theoretical": achieved_tf / fp32_theory,
                 "flops_per_ray": f_isect, "flops_per_bounce": F_SHADE[mode],
                 "avg_launch_ms": per_launch_ms, "launches_per_step": int(stats.iterations),
-                "traffic": None,
+                "traffic": traffic_per_launch(workload, int(stats.iterations)),
                 "queue": {"bound": "hbm", "achieved": qbytes / (k_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                           "frac": qbytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
                           "note": "path records through the wavefront queues x 48 B (a slot advances several bounces per launch in registers)"}}
