@@ -319,7 +319,7 @@ def main():
                 host = host_pinned.numpy()
         else:
             ctx.render(params)
-            host, _ = ctx.readback(out=host_img)                            # D2H inside pt_readback
+            host, _ = ctx.readback_view()                                   # D2H inside pt_readback_view (context-owned pinned image)
         if world > 1:
             dist.barrier()
         return time.perf_counter() - t0, host
@@ -389,7 +389,7 @@ def main():
             "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
             "clocks": clocks, "gpu_launches": int(launches_all),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback (FP64 image device->host) per step, wall clock"},
+                    "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback_view (FP64 mean image device->pinned host) per step, wall clock"},
             "roofline": roofline}
     if single_ms:
         line["strong_scaling"] = {"single_gpu_ms_per_step": single_ms, "n_gpu_ms_per_step": total_ms / args.steps,

@@ -190,6 +190,11 @@ int pt_render_into(pt_ctx *ctx, const pt_render_params *params, void *dev_rgb_su
  * of squared sample radiance when collect_stats was set.  stats may be NULL. */
 int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats);
 
+/* Zero-copy variant: returns the same per-pixel mean image in page-locked host memory OWNED BY THE CONTEXT (one DMA
+ * from the device, no host-side copy).  The pointer stays valid until the next pt_readback_view / pt_destroy on this
+ * context; NULL on error (pt_last_error).  A host loop such as src/smallpt.cpp:538 can read it in place. */
+const double *pt_readback_view(pt_ctx *ctx, pt_stats *stats);
+
 /* Resume from a checkpoint: load per-pixel SUMS (and optionally sums of squares) of `spp_done` samples — what
  * pt_accum_download returned earlier, possibly in another process — into the context's accumulators, so that a
  * following pt_render with accumulate = 1 and sample_offset = spp_done continues the image.  Values must be the

@@ -283,7 +283,7 @@ def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, s
 # ------------------------------------------------------------------------------ product library
 _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
-EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_accum_device_ptr",
+EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
            "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_destroy", "pt_last_error", "pt_version"]
 
@@ -300,6 +300,8 @@ def lib():
         L.pt_render.argtypes = [vp, C.POINTER(RenderParams)]
         L.pt_render_into.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
         L.pt_readback.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(Stats)]
+        L.pt_readback_view.argtypes = [vp, C.POINTER(Stats)]
+        L.pt_readback_view.restype = C.POINTER(C.c_double)
         L.pt_accum_upload.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
         L.pt_accum_download.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.pt_accum_device_ptr.argtypes = [vp]
@@ -390,6 +392,15 @@ class Context:
         if want_sumsq:
             return mean, sq.reshape(p.height, p.width, 3), st
         return mean, st
+
+    def readback_view(self):
+        """Mean image as a numpy VIEW of the context's pinned host buffer (no copy; valid until the next call)."""
+        p = self.last
+        st = Stats()
+        ptr = lib().pt_readback_view(self._h, C.byref(st))
+        if not ptr:
+            self._check(-3, "pt_readback_view")
+        return np.ctypeslib.as_array(ptr, shape=(p.height, p.width, 3)), st
 
     def stats_raw(self):
         """pt_stats without requiring a finished render (debug entries update `specialised`)."""

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "pt_internal.h"
 
@@ -416,25 +417,66 @@ __global__ void k_scale(const double *__restrict__ in, double *__restrict__ out,
     if (i < n) out[i] = in[i] * scale;
 }
 
-// device -> caller's (pageable) buffer through two pinned staging blocks: the copy of block k+1 over PCIe overlaps the
-// host memcpy of block k
-static int staged_d2h(pt_ctx *ctx, double *dst, const double *d_src, size_t n)
+// device -> caller's (pageable) buffer.  Each LANE owns a stream and two pinned staging blocks: the copy of block k+1
+// over PCIe overlaps the host memcpy of block k.  One lane's memcpy (~10 GB/s) is slower than PCIe, so images of 4 MB
+// and more are split over PT_STAGE_LANES lanes, each driven by its own host thread.
+static cudaError_t lane_d2h(pt_ctx *ctx, int lane, double *dst, const double *d_src, size_t n)
 {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return e;
+    PtStageLane &L = ctx->lane[lane];
     const size_t blk = PT_STAGE_ELEMS;
     const size_t nblk = (n + blk - 1) / blk;
     auto issue = [&](size_t k) {
         const size_t off = k * blk, cnt = std::min(blk, n - off);
-        cudaError_t e = cudaMemcpyAsync(ctx->h_stage + (k & 1) * blk, d_src + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_stage[k & 1], ctx->stream);
-        return e;
+        cudaError_t e2 = cudaMemcpyAsync(L.h_stage + (k & 1) * blk, d_src + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, L.stream);
+        if (e2 == cudaSuccess) e2 = cudaEventRecord(L.ev[k & 1], L.stream);
+        return e2;
     };
-    if (nblk) PT_CUDA(ctx, issue(0));
+    if (nblk && (e = issue(0)) != cudaSuccess) return e;
     for (size_t k = 0; k < nblk; k++) {
-        if (k + 1 < nblk) PT_CUDA(ctx, issue(k + 1));
-        PT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[k & 1]));
+        if (k + 1 < nblk && (e = issue(k + 1)) != cudaSuccess) return e;
+        if ((e = cudaEventSynchronize(L.ev[k & 1])) != cudaSuccess) return e;
         const size_t off = k * blk, cnt = std::min(blk, n - off);
-        std::memcpy(dst + off, ctx->h_stage + (k & 1) * blk, cnt * sizeof(double));
+        std::memcpy(dst + off, L.h_stage + (k & 1) * blk, cnt * sizeof(double));
     }
+    return cudaSuccess;
+}
+
+static int staged_d2h(pt_ctx *ctx, double *dst, const double *d_src, size_t n)
+{
+    for (int l = 0; l < PT_STAGE_LANES; l++) {          // lanes are created on first use
+        PtStageLane &L = ctx->lane[l];
+        if (L.stream) continue;
+        PT_CUDA(ctx, cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        PT_CUDA(ctx, cudaMallocHost(&L.h_stage, 2 * PT_STAGE_ELEMS * sizeof(double)));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev[0], cudaEventDisableTiming));
+        PT_CUDA(ctx, cudaEventCreateWithFlags(&L.ev[1], cudaEventDisableTiming));
+    }
+    // the lanes' streams start after everything queued on the context's stream (the sum -> mean kernel)
+    if (!ctx->ev_rb) PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rb, cudaEventDisableTiming));
+    PT_CUDA(ctx, cudaEventRecord(ctx->ev_rb, ctx->stream));
+    const int lanes = n >= 4 * PT_STAGE_ELEMS ? PT_STAGE_LANES : 1;
+    for (int l = 0; l < lanes; l++) PT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_rb, 0));
+    if (lanes == 1) {
+        cudaError_t e = lane_d2h(ctx, 0, dst, d_src, n);
+        if (e != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_readback: ") + cudaGetErrorString(e));
+        return PT_OK;
+    }
+    // contiguous parts, block-aligned
+    const size_t per = ((n + lanes - 1) / lanes + PT_STAGE_ELEMS - 1) / PT_STAGE_ELEMS * PT_STAGE_ELEMS;
+    cudaError_t err[PT_STAGE_LANES];
+    std::thread th[PT_STAGE_LANES];
+    for (int l = 0; l < lanes; l++) {
+        const size_t off = std::min(n, (size_t)l * per), cnt = std::min(per, n - off);
+        err[l] = cudaSuccess;
+        if (l == 0 || cnt == 0) continue;
+        th[l] = std::thread([=, &err] { err[l] = lane_d2h(ctx, l, dst + off, d_src + off, cnt); });
+    }
+    err[0] = lane_d2h(ctx, 0, dst, d_src, std::min(per, n));
+    for (int l = 1; l < lanes; l++) if (th[l].joinable()) th[l].join();
+    for (int l = 0; l < lanes; l++)
+        if (err[l] != cudaSuccess) return pt_fail(ctx, PT_ERR_CUDA, std::string("pt_readback: ") + cudaGetErrorString(err[l]));
     return PT_OK;
 }
 
@@ -445,16 +487,12 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
     const pt_render_params &p = ctx->last;
     const size_t n = (size_t)p.width * p.height * 3;
-    if ((rgb_mean || rgb_sumsq) && !ctx->h_stage) {             // pinned staging: D2H at full PCIe rate
-        PT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, 2 * PT_STAGE_ELEMS * sizeof(double)));
-        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming));
-        PT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming));
-    }
     if (rgb_mean) {
         const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
         if (p.spp > 0) {
             if (ctx->mean_elems < n) {
                 if (ctx->d_mean) cudaFree(ctx->d_mean);
+    if (ctx->h_view) cudaFreeHost(ctx->h_view);
                 ctx->d_mean = nullptr; ctx->mean_elems = 0;
                 PT_CUDA(ctx, cudaMalloc(&ctx->d_mean, n * sizeof(double)));
                 ctx->mean_elems = n;
@@ -539,6 +577,37 @@ int pt_accum_download(pt_ctx *ctx, double *rgb_sum, double *rgb_sumsq, int *spp_
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (spp_done) *spp_done = (int)ctx->accum_spp;
     return PT_OK;
+}
+
+// Zero-copy read-back: the mean image in library-owned pinned host memory (one DMA, no host memcpy).
+const double *pt_readback_view(pt_ctx *ctx, pt_stats *stats)
+{
+    if (!ctx) { pt_fail(ctx, PT_ERR_ARG, "null context"); return nullptr; }
+    if (!ctx->rendered) { pt_fail(ctx, PT_ERR_STATE, "pt_readback_view before a successful pt_render"); return nullptr; }
+    auto bad = [&](cudaError_t e, const char *what) { pt_fail(ctx, PT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); return (const double *)nullptr; };
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return bad(e, "cudaSetDevice");
+    const pt_render_params &p = ctx->last;
+    const size_t n = (size_t)p.width * p.height * 3;
+    if (ctx->view_elems < n) {
+        if (ctx->h_view) cudaFreeHost(ctx->h_view);
+        ctx->h_view = nullptr; ctx->view_elems = 0;
+        if ((e = cudaMallocHost(&ctx->h_view, n * sizeof(double))) != cudaSuccess) return bad(e, "cudaMallocHost");
+        ctx->view_elems = n;
+    }
+    if (ctx->mean_elems < n) {
+        if (ctx->d_mean) cudaFree(ctx->d_mean);
+        ctx->d_mean = nullptr; ctx->mean_elems = 0;
+        if ((e = cudaMalloc(&ctx->d_mean, n * sizeof(double))) != cudaSuccess) return bad(e, "cudaMalloc");
+        ctx->mean_elems = n;
+    }
+    const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
+    const double spp = (double)(ctx->accum_spp > 0 ? ctx->accum_spp : p.spp);
+    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, spp > 0 ? 1.0 / spp : 1.0);
+    if ((e = cudaMemcpyAsync(ctx->h_view, ctx->d_mean, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bad(e, "cudaStreamSynchronize");
+    if (stats) *stats = ctx->stats;
+    return ctx->h_view;
 }
 
 void *pt_accum_device_ptr(pt_ctx *ctx) { return ctx ? (void *)(ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum) : nullptr; }
@@ -631,15 +700,20 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_sum) cudaFree(ctx->d_sum);
     if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
     if (ctx->d_mean) cudaFree(ctx->d_mean);
-    if (ctx->ev_stage[0]) cudaEventDestroy(ctx->ev_stage[0]);
-    if (ctx->ev_stage[1]) cudaEventDestroy(ctx->ev_stage[1]);
+    if (ctx->ev_rb) cudaEventDestroy(ctx->ev_rb);
+    for (int l = 0; l < PT_STAGE_LANES; l++) {
+        PtStageLane &L = ctx->lane[l];
+        if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+        if (L.ev[0]) cudaEventDestroy(L.ev[0]);
+        if (L.ev[1]) cudaEventDestroy(L.ev[1]);
+        if (L.h_stage) cudaFreeHost(L.h_stage);
+    }
     if (ctx->d_objs) cudaFree(ctx->d_objs);
     if (ctx->d_mats) cudaFree(ctx->d_mats);
     if (ctx->d_sphf) cudaFree(ctx->d_sphf);
     if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev_batch[0]) cudaEventDestroy(ctx->ev_batch[0]);
     if (ctx->ev_batch[1]) cudaEventDestroy(ctx->ev_batch[1]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -24,10 +24,16 @@ struct DevObj64 {
 
 // ------------------------------------------------------------------ context
 struct PtJitKernel;
+#define PT_STAGE_LANES 3
+struct PtStageLane {                  // one read-back pipeline: its own stream, two pinned blocks of PT_STAGE_ELEMS doubles
+    cudaStream_t stream = nullptr;
+    double *h_stage = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+};
 #ifndef PT_JIT_SPH_IMM_MAX
 #define PT_JIT_SPH_IMM_MAX 256          /* specialised build: sphere scan tables up to this size become immediates */
 #endif
-#define PT_STAGE_ELEMS ((size_t)1 << 19)   /* 4 MB staging blocks */
+#define PT_STAGE_ELEMS ((size_t)1 << 17)   /* 1 MB staging blocks */
 #define PT_JIT_MIN_PATHS (1ull << 25)   /* renders at least this big are worth a ~1 s specialised build (jit_mode 1) */
 
 struct pt_ctx {
@@ -68,10 +74,12 @@ struct pt_ctx {
     unsigned int *h_pinned = nullptr;                  // 2 pinned words for the termination check
     cudaEvent_t ev_batch[2] = {nullptr, nullptr};
     DevStats *h_stats = nullptr;                       // pinned
-    double *h_stage = nullptr;                         // pinned staging for pt_readback: two blocks of PT_STAGE_ELEMS
-    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rb = nullptr;                       // orders the read-back lanes after the context's stream
+    PtStageLane lane[PT_STAGE_LANES];                  // pt_readback: device -> pinned staging -> caller's buffer
     double *d_mean = nullptr;                          // per-pixel mean (sum / spp), produced on the device at readback
     size_t mean_elems = 0;
+    double *h_view = nullptr;                          // pinned host image handed out by pt_readback_view
+    size_t view_elems = 0;
     DevStats *d_stats = nullptr;
     pt_stats stats{};
     // scene specialisation: 0 = generic kernel only, 1 = specialise renders of >= PT_JIT_MIN_PATHS paths, 2 = always

@@ -227,3 +227,14 @@ def test_small_renders_that_exhaust_generation_inside_the_first_launch():
                     c.render(ptb.params(w, h, spp, mode=mode, seed=spp, queue_capacity=8192, bounces_per_launch=3))
                     small, _ = c.readback()
                     assert np.array_equal(full, small), (scene, mode, spec, spp)
+
+
+def test_readback_view_equals_readback():
+    w, h = 200, 120
+    with ptb.Context(ptb.builtin_scene("A", w, h)) as c:
+        c.render(ptb.params(w, h, 8, mode=0, seed=4))
+        a, st = c.readback()
+        v, st2 = c.readback_view()
+        assert np.array_equal(a, v) and st.paths == st2.paths == w * h * 8
+        c.render(ptb.params(w, h, 4, mode=0, seed=4, sample_offset=8, accumulate=1))
+        assert np.array_equal(c.readback()[0], c.readback_view()[0])
