@@ -324,6 +324,7 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode > 0) {
         // scene-specialised kernel: built (once per scene/mode) BEFORE the timed region starts
         const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp / (unsigned long long)world;
+        // (which build runs depends on the render's size only; the two builds give bit-identical images anyway — tested)
         if (ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS) ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0);
     }
     PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
@@ -395,7 +396,7 @@ int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t 
         if (spec_out && spec_cap) { std::strncpy(spec_out, spec.c_str(), spec_cap - 1); spec_out[spec_cap - 1] = 0; }
         std::vector<char> cubin;
         std::string log;
-        rc = pt_jit_compile(spec, cubin, log, seconds);
+        rc = pt_jit_build(spec, cubin, log, seconds, nullptr);
         if (rc != PT_OK) rc = pt_fail(nullptr, rc, "NVRTC: " + log);
         else if (cubin_bytes) *cubin_bytes = cubin.size();
     }

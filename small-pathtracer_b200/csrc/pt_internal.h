@@ -34,7 +34,7 @@ struct PtStageLane {                  // one read-back pipeline: its own stream,
 #define PT_JIT_SPH_IMM_MAX 256          /* specialised build: sphere scan tables up to this size become immediates */
 #endif
 #define PT_STAGE_ELEMS ((size_t)1 << 17)   /* 1 MB staging blocks */
-#define PT_JIT_MIN_PATHS (1ull << 25)   /* renders at least this big are worth a ~1 s specialised build (jit_mode 1) */
+#define PT_JIT_MIN_PATHS (1ull << 25)   /* jit_mode 1: renders at least this big use the specialised build (NVRTC ~0.5 s once, or the disk cache) */
 
 struct pt_ctx {
     int device = 0;
@@ -101,6 +101,7 @@ struct PtJitKernel {
 std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false);
 int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
 PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false);
+int pt_jit_build(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds, bool *from_disk);
 #define PT_CUDA(ctx, call)                                                                      \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \

@@ -19,6 +19,11 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
+
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "pt_internal.h"
 #include "pt_kernel_src.h"
@@ -191,6 +196,77 @@ int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::strin
     return PT_OK;
 }
 
+// ---- disk cache of built modules: $PTB200_CACHE_DIR, else $XDG_CACHE_HOME/ptb200, else $HOME/.cache/ptb200 ("off" disables).
+// Key = FNV-1a of the specialisation header, the embedded kernel source and the NVRTC options: any change of the
+// library's device code or of the scene gives another file.
+static std::string cache_dir()
+{
+    const char *e = std::getenv("PTB200_CACHE_DIR");
+    std::string d;
+    if (e) { if (!*e || std::string(e) == "off") return ""; d = e; }
+    else if (const char *x = std::getenv("XDG_CACHE_HOME")) d = std::string(x) + "/ptb200";
+    else if (const char *h = std::getenv("HOME")) d = std::string(h) + "/.cache/ptb200";
+    else return "";
+    std::string partial;
+    for (size_t i = 0; i <= d.size(); i++) {             // mkdir -p
+        if (i == d.size() || d[i] == '/') { if (!partial.empty()) ::mkdir(partial.c_str(), 0755); }
+        if (i < d.size()) partial += d[i];
+    }
+    struct stat st;
+    if (::stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) return "";
+    return d;
+}
+
+static std::string cache_path(const std::string &spec)
+{
+    const std::string dir = cache_dir();
+    if (dir.empty()) return "";
+    unsigned long long hsh = 1469598103934665603ull;
+    auto mix = [&](const char *p, size_t n) { for (size_t i = 0; i < n; i++) { hsh ^= (unsigned char)p[i]; hsh *= 1099511628211ull; } };
+    mix(spec.data(), spec.size());
+    mix(PT_KERNEL_SRC, sizeof(PT_KERNEL_SRC));
+    if (const char *o = std::getenv("PTB200_JIT_OPTS")) mix(o, std::strlen(o));
+    char b[64];
+    std::snprintf(b, sizeof b, "/ptb200-%016llx.cubin", hsh);
+    return dir + b;
+}
+
+// Cubin for a specialisation: from the disk cache when present, else NVRTC (and the result is stored).
+int pt_jit_build(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds, bool *from_disk)
+{
+    if (from_disk) *from_disk = false;
+    const std::string path = std::getenv("PTB200_JIT_KEEP_SRC") || std::getenv("PTB200_JIT_DUMP") ? std::string() : cache_path(spec);
+    if (!path.empty()) {
+        if (FILE *f = std::fopen(path.c_str(), "rb")) {
+            std::fseek(f, 0, SEEK_END);
+            const long sz = std::ftell(f);
+            std::fseek(f, 0, SEEK_SET);
+            if (sz > 1024) {
+                cubin.resize((size_t)sz);
+                const size_t got = std::fread(cubin.data(), 1, (size_t)sz, f);
+                std::fclose(f);
+                if (got == (size_t)sz && std::memcmp(cubin.data(), "\x7f" "ELF", 4) == 0) {
+                    if (from_disk) *from_disk = true;
+                    if (seconds) *seconds = 0;
+                    return PT_OK;
+                }
+            } else std::fclose(f);
+        }
+    }
+    int rc = pt_jit_compile(spec, cubin, log, seconds);
+    if (rc == PT_OK && !path.empty()) {                   // write-then-rename: concurrent ranks never see a partial file
+        char tmp[64];
+        std::snprintf(tmp, sizeof tmp, ".tmp%d", (int)::getpid());
+        const std::string t = path + tmp;
+        if (FILE *f = std::fopen(t.c_str(), "wb")) {
+            const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            std::fclose(f);
+            if (!ok || std::rename(t.c_str(), path.c_str()) != 0) std::remove(t.c_str());
+        }
+    }
+    return rc;
+}
+
 // The specialised kernel for the context's current scene, or nullptr (generic kernel) when JIT is off/unavailable.
 PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
 {
@@ -203,7 +279,8 @@ PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
     std::vector<char> cubin;
     std::string log;
     double secs = 0;
-    if (pt_jit_compile(spec, cubin, log, &secs) == PT_OK) {
+    bool from_disk = false;
+    if (pt_jit_build(spec, cubin, log, &secs, &from_disk) == PT_OK) {
         jk = new PtJitKernel();
         jk->compile_seconds = secs;
         cudaError_t e = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -220,7 +297,7 @@ PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
         ctx->jit_note = "generic kernel (" + log.substr(0, 300) + ")";
         if (std::getenv("PTB200_JIT_VERBOSE")) std::fprintf(stderr, "[ptb200] JIT unavailable: %s\n", log.c_str());
     } else if (std::getenv("PTB200_JIT_VERBOSE")) {
-        std::fprintf(stderr, "[ptb200] scene-specialised k_bounce (mode %d) compiled in %.2f s\n", mode, secs);
+        std::fprintf(stderr, "[ptb200] scene-specialised k_bounce (mode %d) %s in %.2f s\n", mode, from_disk ? "loaded from the disk cache" : "compiled", secs);
     }
     g_cache[spec] = jk;
     return jk;

@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# hermetic tests: every specialisation is really built by NVRTC (the disk cache has its own test)
+os.environ.setdefault("PTB200_CACHE_DIR", "off")
+
 from _pkg import ptb  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")

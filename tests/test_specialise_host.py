@@ -37,3 +37,18 @@ def test_header_carries_the_scene_constants():
     assert re.search(r"#define PT_J_lxw \(0x1\.2p\+5f\)", spec) and re.search(r"#define PT_J_larea \(0x1\.44p\+10f\)", spec)
     other, _, _ = ptb.specialise(ptb.builtin_scene("C", 64, 64), 0)
     assert other != spec
+
+
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+def test_disk_cache_serves_the_second_process(tmp_path):
+    import os, subprocess, sys
+    from conftest import ROOT
+    code = ("import sys; sys.path.insert(0, %r); from _pkg import ptb; "
+            "print(ptb.specialise(ptb.builtin_scene('C', 64, 64), 1)[1:])" % ROOT)
+    env = dict(os.environ, PTB200_CACHE_DIR=str(tmp_path / "cache"))
+    first = eval(subprocess.check_output([sys.executable, "-c", code], env=env, text=True))
+    files = os.listdir(tmp_path / "cache")
+    assert len(files) == 1 and files[0].startswith("ptb200-") and files[0].endswith(".cubin")
+    second = eval(subprocess.check_output([sys.executable, "-c", code], env=env, text=True))
+    assert first[0] == second[0] and first[1] > 0.05 and second[1] == 0.0      # same cubin, no NVRTC the second time
+    assert open(tmp_path / "cache" / files[0], "rb").read(4) == b"\x7fELF"
