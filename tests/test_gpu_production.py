@@ -222,3 +222,67 @@ def test_default_policy_depends_on_the_render_size_only():
             imgs.append(c.readback()[0])
         assert flags == [0, 1, 0, 1], flags
         assert np.array_equal(imgs[0], imgs[2]) and np.array_equal(imgs[1], imgs[3])
+
+
+def _shelf_scene(n_shelves, w, h):
+    """The built-in room plus a stack of thin horizontal shelves: more rectangles of one axis class than the 16 unrolled
+    slots hold, so the overflow loop of closest_hit is exercised (objects in id order: the 17 of scene A, then shelves)."""
+    base = ptb.builtin_scene("A", w, h)
+    planes = [base.planes[i] for i in range(base.n_planes)]
+    for k in range(n_shelves):
+        planes.append(ptb.rect(ptb.PT_PLANE_XZ, 45 + (k % 3), 60 + (k % 5), 100 + k, 110 + k, 5.0 + 2.5 * k, c=(.6, .7, .8)))
+    return ptb.Scene([], planes, list(range(len(planes))), base.light, base.camera)
+
+
+def test_fp32_engine_edge_cases():
+    # sizes: one pixel, zero samples, a rank that owns no rows, ragged last tile
+    sc = ptb.builtin_scene("A", 1, 1)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(1, 1, 5, mode=0))
+        mean, st = c.readback()
+        assert mean.shape == (1, 1, 3) and st.paths == 5 and np.isfinite(mean).all()
+        c.render(ptb.params(1, 1, 0, mode=0))
+        mean, st = c.readback()
+        assert not mean.any() and st.paths == 0
+    w, h = 40, 21
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(w, h, 8, mode=1, seed=2))
+        full, _ = c.readback()
+        total = np.zeros_like(full)
+        for rank in range(5):                                  # 3 tiles of 8 rows (the last one ragged) over 5 ranks
+            c.render(ptb.params(w, h, 8, mode=1, seed=2, tile_rows=8, rank=rank, world=5))
+            part, st = c.readback()
+            assert st.paths == (0 if rank >= 3 else (8 if rank < 2 else 5) * w * 8)
+            total += part
+        assert np.array_equal(total, full)
+        # max_depth cuts paths and counts them
+        c.render(ptb.params(w, h, 16, mode=1, max_depth=3))
+        cut, st = c.readback()
+        assert st.truncated > 0 and st.max_depth_seen <= 3 and np.isfinite(cut).all()
+    # more objects than the FP32 constant layout holds: a clear error, and the FP64 engine still renders
+    many = [ptb.sphere(0.5, (10 + (i % 30) * 2.5, 5 + (i // 30) * 3.0, 60), c=(.5, .5, .5)) for i in range(600)]
+    big = ptb.Scene(many, [], [~i for i in range(600)], ptb.Light(), sc.camera)
+    with ptb.Context(big) as c:
+        with pytest.raises(ptb.PtError, match="512 objects"):
+            c.render(ptb.params(w, h, 1, mode=1))
+        c.render(ptb.params(8, 4, 1, mode=1, engine=ptb.PT_ENGINE_FP64_ERAND48))
+
+
+def test_overflow_rectangles_generic_and_specialised():
+    # 17 + 24 rectangles, 29 of them in the XZ class (16 unrolled slots + 13 in the overflow loop)
+    w, h = 96, 72
+    sc = _shelf_scene(24, w, h)
+    from conftest import room_rays
+    rays = room_rays(100000, 3, f32_exact=True, margin=2.0)
+    t_o, id_o = ptb.oracle_intersect(sc, rays)
+    assert (id_o >= 17).mean() > 0.01                           # the shelves are hit
+    imgs = []
+    with ptb.Context(sc) as c:
+        for spec in (0, 2):
+            c.set_specialisation(spec)
+            t, ids = c.intersect(rays, 32)
+            assert (ids == id_o).mean() > 0.9995
+            c.render(ptb.params(w, h, 32, mode=0, seed=8))
+            imgs.append(c.readback()[0])
+    assert np.array_equal(imgs[0], imgs[1])
