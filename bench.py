@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--assembly", default="auto", choices=["auto", "nccl"], help="N > 1: auto = peer-memory stores when CUDA IPC works, else NCCL gather")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra C4 (intersection-bound) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -253,16 +254,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # N > 1: every rank's resolve kernel stores its row tiles straight into rank 0's image over NVLink peer memory
+    # (dist.SharedImage); where CUDA IPC is unavailable, pack + NCCL gather + de-interleave (dist.gather_rows)
+    shared, assembly = None, "single GPU"
+    if world > 1:
+        try:
+            if args.assembly == "nccl":
+                raise RuntimeError("NCCL gather requested")
+            shared = pdist.SharedImage(ctx, h, w, rank, world, dst=0)
+            assembly = "peer-memory stores from the resolve kernel (CUDA IPC over NVLink) + one barrier"
+        except RuntimeError:
+            shared, assembly = None, "pack + NCCL gather to rank 0 + de-interleave"
+
     def step(timed):
-        """one render of this rank's tiles + gather to rank 0; returns (device ms, stats)"""
+        """one render of this rank's tiles + assembly on rank 0; returns (device ms, stats)"""
         flush.fill_(1)                                                    # L2 flush between iterations
         stream.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        local = torch.empty((h, w, 3), dtype=torch.float64, device=device)
-        e0.record(stream)
-        ctx.render_into(params, local.data_ptr(), stream.cuda_stream)
-        st = ctx.stats()
-        full = pdist.gather_rows(local, h, tile_rows, rank, world, dst=0) if world > 1 else local
+        if shared is not None:
+            e0.record(stream)
+            full = shared.render(params, stream.cuda_stream)
+            st = ctx.stats()
+        else:
+            local = torch.empty((h, w, 3), dtype=torch.float64, device=device)
+            e0.record(stream)
+            ctx.render_into(params, local.data_ptr(), stream.cuda_stream)
+            st = ctx.stats()
+            full = pdist.gather_rows(local, h, tile_rows, rank, world, dst=0) if world > 1 else local
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)              # render (all k_bounce launches + resolve) + gather, on `stream`
@@ -311,7 +329,10 @@ def main():
         t0 = time.perf_counter()
         ctx.update_scene(scene)                                             # H2D: scene table + camera (pt_scene_upload, in place)
         if world > 1:
-            full, local = pdist.render_sharded(ctx, params, device, dst=0)
+            if shared is not None:
+                full = shared.render(params, stream.cuda_stream)
+            else:
+                full, local = pdist.render_sharded(ctx, params, device, dst=0)
             host = None
             if rank == 0:                                                   # D2H: assembled image (sum -> mean on the device)
                 host_pinned.copy_(full / float(spp), non_blocking=True)
@@ -380,7 +401,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "engine": "FP32 Philox wavefront", "tile_rows": tile_rows, "parallelism": f"row-tiles x{world}",
+            "config": {"workload": desc, "engine": "FP32 Philox wavefront", "tile_rows": tile_rows, "parallelism": f"row-tiles x{world}", "assembly": assembly,
                        "l2": "256 MiB flush write between timed iterations", "paths_per_step": paths / args.steps,
                        "rays_per_path": rays / paths, "seed": 0,
                        "kernel": ("scene-specialised k_bounce (NVRTC build with the scene constants as immediates, compiled once during warm-up)"

@@ -134,6 +134,11 @@ typedef struct pt_render_params {
      * are integers, so any split of the sample range gives the bit-identical image; pt_readback divides by the total. */
     int      sample_offset;
     int      accumulate;
+    /* Multi-GPU assembly without a gather (pt_render_into): 1 = write ONLY the rows this rank owns and leave the rest
+     * of the target untouched, so that all ranks can render straight into ONE image — rank 0's buffer, opened by the
+     * other processes through pt_ipc_open and written over NVLink peer memory by the resolve kernel. */
+    int      owned_rows_only;
+    int      _pad;
 } pt_render_params;
 
 typedef struct pt_stats {
@@ -189,6 +194,16 @@ int pt_render_into(pt_ctx *ctx, const pt_render_params *params, void *dev_rgb_su
  * toInt (:319-321).  rgb_sumsq (optional, may be NULL) receives per-pixel per-channel sums
  * of squared sample radiance when collect_stats was set.  stats may be NULL. */
 int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stats);
+
+/* Peer-memory plumbing for the fused resolve + gather (one process per GPU on one node).  pt_device_alloc returns a
+ * cudaMalloc'ed buffer on the context's device (IPC handles name whole allocations, so a framework's sub-allocated
+ * tensor will not do); pt_ipc_export / pt_ipc_open wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle (peer access is
+ * enabled lazily); handle = 64 opaque bytes to ship to the other processes by any means. */
+int pt_device_alloc(pt_ctx *ctx, size_t bytes, void **dev_ptr);
+int pt_device_free(pt_ctx *ctx, void *dev_ptr);
+int pt_ipc_export(pt_ctx *ctx, const void *dev_ptr, unsigned char handle[64]);
+int pt_ipc_open(pt_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int pt_ipc_close(pt_ctx *ctx, void *dev_ptr);
 
 /* Zero-copy variant: returns the same per-pixel mean image in page-locked host memory OWNED BY THE CONTEXT (one DMA
  * from the device, no host-side copy).  The pointer stays valid until the next pt_readback_view / pt_destroy on this

@@ -59,7 +59,7 @@ class RenderParams(C.Structure):
                 ("engine", C.c_int), ("sincos", C.c_int), ("seed", C.c_uint64),
                 ("tile_rows", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("max_depth", C.c_int),
                 ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("bounces_per_launch", C.c_int),
-                ("sample_offset", C.c_int), ("accumulate", C.c_int)]
+                ("sample_offset", C.c_int), ("accumulate", C.c_int), ("owned_rows_only", C.c_int), ("_pad", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -271,12 +271,12 @@ def write_ppm(path, rgb_mean, w, h):
 
 def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, sincos=PT_SINCOS_LIBM, seed=0,
            tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0, bounces_per_launch=0,
-           sample_offset=0, accumulate=0):
+           sample_offset=0, accumulate=0, owned_rows_only=0):
     p = RenderParams()
     p.width, p.height, p.spp, p.mode, p.engine, p.sincos, p.seed = w, h, spp, mode, engine, sincos, seed
     p.tile_rows, p.rank, p.world, p.max_depth = tile_rows, rank, world, max_depth
     p.queue_capacity, p.collect_stats, p.bounces_per_launch = queue_capacity, collect_stats, bounces_per_launch
-    p.sample_offset, p.accumulate = sample_offset, accumulate
+    p.sample_offset, p.accumulate, p.owned_rows_only = sample_offset, accumulate, owned_rows_only
     return p
 
 
@@ -285,7 +285,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
-           "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -300,6 +300,11 @@ def lib():
         L.pt_render.argtypes = [vp, C.POINTER(RenderParams)]
         L.pt_render_into.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
         L.pt_readback.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(Stats)]
+        L.pt_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.pt_device_free.argtypes = [vp, vp]
+        L.pt_ipc_export.argtypes = [vp, vp, C.c_char_p]
+        L.pt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.pt_ipc_close.argtypes = [vp, vp]
         L.pt_readback_view.argtypes = [vp, C.POINTER(Stats)]
         L.pt_readback_view.restype = C.POINTER(C.c_double)
         L.pt_accum_upload.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
@@ -401,6 +406,28 @@ class Context:
         if not ptr:
             self._check(-3, "pt_readback_view")
         return np.ctypeslib.as_array(ptr, shape=(p.height, p.width, 3)), st
+
+    # ---- peer-memory plumbing (fused resolve + gather, dist.SharedImage)
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(lib().pt_device_alloc(self._h, nbytes, C.byref(p)), "pt_device_alloc")
+        return p.value
+
+    def device_free(self, ptr):
+        self._check(lib().pt_device_free(self._h, C.c_void_p(ptr)), "pt_device_free")
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._check(lib().pt_ipc_export(self._h, C.c_void_p(ptr), buf), "pt_ipc_export")
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._check(lib().pt_ipc_open(self._h, C.c_char_p(handle), C.byref(p)), "pt_ipc_open")
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._check(lib().pt_ipc_close(self._h, C.c_void_p(ptr)), "pt_ipc_close")
 
     def stats_raw(self):
         """pt_stats without requiring a finished render (debug entries update `specialised`)."""

@@ -312,7 +312,7 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     }
     double *d_sum = ext_sum ? ext_sum : ctx->d_sum;
     ctx->d_sum_ext = ext_sum;
-    PT_CUDA(ctx, cudaMemsetAsync(d_sum, 0, n_acc * sizeof(double), s));
+    if (!p->owned_rows_only) PT_CUDA(ctx, cudaMemsetAsync(d_sum, 0, n_acc * sizeof(double), s));   // owned_rows_only: other ranks write the rest
     if (p->collect_stats) PT_CUDA(ctx, cudaMemsetAsync(ctx->d_sumsq, 0, n_acc * sizeof(double), s));
     PT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, sizeof(DevStats), s));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -409,6 +409,51 @@ int pt_render_into(pt_ctx *ctx, const pt_render_params *p, void *dev_rgb_sum, vo
 {
     if (!dev_rgb_sum) return pt_fail(ctx, PT_ERR_ARG, "null device buffer");
     return render_common(ctx, p, (double *)dev_rgb_sum, (cudaStream_t)stream);
+}
+
+int pt_device_alloc(pt_ctx *ctx, size_t bytes, void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || bytes == 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaMalloc(dev_ptr, bytes));
+    return PT_OK;
+}
+
+int pt_device_free(pt_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return PT_ERR_ARG;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaFree(dev_ptr));
+    return PT_OK;
+}
+
+int pt_ipc_export(pt_ctx *ctx, const void *dev_ptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ctx || !dev_ptr || !handle) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    PT_CUDA(ctx, cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    std::memcpy(handle, &h, 64);
+    return PT_OK;
+}
+
+int pt_ipc_open(pt_ctx *ctx, const unsigned char handle[64], void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || !handle) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    PT_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PT_OK;
+}
+
+int pt_ipc_close(pt_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx) return PT_ERR_ARG;
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
+    return PT_OK;
 }
 
 // per-pixel SUM -> MEAN on the device (the division by `samps` of src/smallpt.cpp:536), so the host only copies

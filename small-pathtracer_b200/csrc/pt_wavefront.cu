@@ -43,6 +43,22 @@ __global__ void k_resolve(const unsigned long long *__restrict__ fix, const unsi
     if (sumsq && fixsq) sumsq[i] = (double)fixsq[i] * PT_FIX_INV;
 }
 
+// the same for the rows of this rank only (owned_rows_only): `sum` may be another GPU's image, written over NVLink
+// peer memory — the gather of the row tiles is these stores
+__global__ void k_resolve_owned(const unsigned long long *__restrict__ fix, double *__restrict__ sum, unsigned long long owned_pixels,
+                                int w, int tile_rows, int rank, int world)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= owned_pixels * 3ull) return;
+    const unsigned long long lp = i / 3ull;
+    const unsigned int ch = (unsigned int)(i - lp * 3ull);
+    const unsigned int row_local = (unsigned int)(lp / (unsigned int)w), x = (unsigned int)(lp - (unsigned long long)row_local * (unsigned int)w);
+    const unsigned int tile = row_local / (unsigned int)tile_rows;
+    const unsigned int y = (tile * (unsigned int)world + (unsigned int)rank) * (unsigned int)tile_rows + (row_local - tile * (unsigned int)tile_rows);
+    const size_t idx = ((size_t)y * (size_t)w + x) * 3 + ch;
+    sum[idx] = (double)fix[idx] * PT_FIX_INV;
+}
+
 __global__ void k_philox2(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,7 +281,12 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         ctx->counts_dirty = (size_t)it + 4;
         it_total = it;
     }
-    k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc);
+    if (p->owned_rows_only && !stats) {
+        if (owned_pixels > 0)
+            k_resolve_owned<<<(unsigned)((owned_pixels * 3ull + 255) / 256), 256, 0, s>>>(ctx->d_fix, d_sum, owned_pixels, w, tile, p->rank, world);
+    } else {
+        k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc);
+    }
     ctx->stats.kernel_launches++;
     PT_CUDA(ctx, cudaGetLastError());
     ctx->stats.queue_slots_io = 0;

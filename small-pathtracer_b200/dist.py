@@ -58,3 +58,82 @@ def render_sharded(ctx, params, device, dst=0, group=None):
     world = params.world if params.world > 0 else 1
     full = gather_rows(local, params.height, params.tile_rows, params.rank, world, dst=dst, group=group)
     return full, local
+
+
+class _CudaArray:
+    """A raw device pointer presented through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape, owner=None):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+        self._owner = owner
+
+
+class SharedImage:
+    """Fused resolve + gather over NVLink peer memory (one process per GPU on one node).
+
+    Rank `dst` owns ONE (H, W, 3) float64 image in device memory (a whole cudaMalloc allocation, so that it has a CUDA IPC
+    handle); the other ranks open it and `pt_render_into(..., owned_rows_only=1)` makes every rank's resolve kernel store
+    its own row tiles straight into that image — there is no pack, no collective and no de-interleave.  The only
+    synchronisation is one barrier after the renders.  Falls back (raises) where CUDA IPC is not available; callers then
+    use `gather_rows`."""
+
+    def __init__(self, ctx, height, width, rank, world, dst=0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.dst, self.group = ctx, rank, world, dst, group
+        self.shape = (height, width, 3)
+        nbytes = height * width * 3 * 8
+        self.ptr = None
+        self.opened = False
+        err = 0
+        handle = bytearray(64)
+        if rank == dst:
+            try:
+                self.ptr = ctx.device_alloc(nbytes)
+                handle = bytearray(ctx.ipc_export(self.ptr))
+            except Exception:               # noqa: BLE001
+                err = 1
+        if world > 1:
+            # the 64-byte handle travels as a CPU tensor over whatever backend the group has (NCCL needs device tensors)
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(handle) + [err], dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=dst, group=group)
+            t = t.cpu()
+            err = int(t[64])
+            if rank != dst and not err:
+                try:
+                    self.ptr = ctx.ipc_open(bytes(t[:64].tolist()))
+                    self.opened = True
+                except Exception:           # noqa: BLE001
+                    err = 1
+            flag = torch.tensor([err], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            err = int(flag.item())
+        if err:
+            self.close()
+            raise RuntimeError("CUDA IPC is not available between these processes")
+        self.tensor = torch.as_tensor(_CudaArray(self.ptr, self.shape, owner=self), device=torch.device("cuda", torch.cuda.current_device())) if rank == dst else None
+
+    def render(self, params, stream=0):
+        """Every rank renders its row tiles into the shared image; returns the assembled tensor (per-pixel sums) on dst."""
+        import torch.distributed as dist
+        params.owned_rows_only = 1
+        try:
+            self.ctx.render_into(params, self.ptr, stream)       # synchronous on return: this rank's stores have landed
+        finally:
+            params.owned_rows_only = 0
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return self.tensor
+
+    def close(self):
+        if self.ptr is None:
+            return
+        try:
+            if self.opened:
+                self.ctx.ipc_close(self.ptr)
+            elif self.rank == self.dst:
+                self.tensor = None
+                self.ctx.device_free(self.ptr)
+        finally:
+            self.ptr = None

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(ptb.Plane) == 8 + 40 + 96 + 16 + 48
     assert C.sizeof(ptb.Camera) == 96
     assert C.sizeof(ptb.Light) == 8 + 48
-    assert C.sizeof(ptb.RenderParams) == 24 + 8 + 16 + 16 + 8
+    assert C.sizeof(ptb.RenderParams) == 24 + 8 + 16 + 16 + 8 + 8
     assert C.sizeof(ptb.Stats) == 72 + 8 + 16 + 8
 
 

@@ -29,3 +29,64 @@ def test_render_into_torch_tensor_and_assemble():
             assert c.accum_ptr() == local.data_ptr()
     assert np.array_equal(out.cpu().numpy() / spp, mean)
     assert np.array_equal(img.cpu().numpy() / spp, mean)
+
+
+def test_owned_rows_only_renders_assemble_in_one_buffer():
+    # the fused resolve + gather, ranks emulated on one GPU: every rank's resolve kernel writes only its own row tiles
+    # into ONE image (a whole cudaMalloc allocation, wrapped as a torch tensor without a copy)
+    import torch
+    from small_pathtracer_b200 import dist as pdist
+    w, h, spp, tile, world = 72, 37, 16, 8, 3       # spp a power of two: sum / spp == sum * (1 / spp) exactly
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(w, h, spp, mode=1, seed=6))
+        mean = c.readback()[0]
+        ptr = c.device_alloc(h * w * 3 * 8)
+        img = torch.as_tensor(pdist._CudaArray(ptr, (h, w, 3)), device=torch.device("cuda:0"))
+        img.fill_(-1.0)                                       # rows nobody owns would stay -1
+        torch.cuda.synchronize()
+        for r in range(world):
+            c.render_into(ptb.params(w, h, spp, mode=1, seed=6, tile_rows=tile, rank=r, world=world, owned_rows_only=1), ptr, 0)
+        got = img.cpu().numpy() / spp
+        del img
+        c.device_free(ptr)
+    assert np.array_equal(got, mean)
+
+
+def _ipc_worker(rank, world, port, w, h, spp, tile, out_path):
+    import os, sys
+    import torch
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from _pkg import ptb as P
+    from small_pathtracer_b200 import dist as pdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)                                  # both processes share the one GPU of the test box
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = P.builtin_scene("A", w, h)
+    with P.Context(sc, device=0) as c:
+        shared = pdist.SharedImage(c, h, w, rank, world, dst=0)
+        for rep in range(2):                                  # the image is re-used across renders
+            full = shared.render(P.params(w, h, spp, mode=0, seed=9 + rep, tile_rows=tile, rank=rank, world=world))
+            if rank == 0:
+                np.save(out_path + str(rep) + ".npy", full.cpu().numpy())
+            dist.barrier()
+        shared.close()
+    dist.destroy_process_group()
+
+
+def test_two_processes_assemble_through_cuda_ipc(tmp_path):
+    # two processes, one GPU: rank 1 opens rank 0's image through its IPC handle and its resolve kernel stores into it
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    w, h, spp, tile = 64, 40, 8, 8
+    out = str(tmp_path / "img")
+    mp.spawn(_ipc_worker, args=(2, port, w, h, spp, tile, out), nprocs=2, join=True)
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        for rep in range(2):
+            c.render(ptb.params(w, h, spp, mode=0, seed=9 + rep))
+            assert np.array_equal(np.load(out + str(rep) + ".npy") / spp, c.readback()[0])

@@ -1,1 +1,1 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s29.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu_s29.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s31.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu_s31.log
