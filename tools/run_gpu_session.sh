@@ -1,1 +1,8 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s31.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu_s31.log
+for N in 8 4; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s32_n$N.json 2> gpurun_out/bench_s32_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s32_n$N.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d.get('strong_scaling'))"
+done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 8 --steps 5 --warmup 3 --assembly nccl > gpurun_out/bench_s32_n8_nccl.json 2> gpurun_out/bench_s32_n8_nccl.err; tail -1 gpurun_out/bench_s32_n8_nccl.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d.get('strong_scaling'))"
