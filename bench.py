@@ -241,7 +241,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    tile_rows = 16 if world > 1 else 8
+    # 10-row tiles: 2160 rows = 216 tiles, the same number of tiles (and rows) for every rank at 2, 4 and 8 GPUs
+    tile_rows = 10 if world > 1 else 8
     scene = ptb.builtin_scene(scene_name, w, h)
     ctx = ptb.Context(scene, device=local_rank)
     params = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=rank, world=world)
