@@ -184,6 +184,12 @@ int pt_scene_upload(pt_ctx **ctx, const pt_scene *scene, int device);
  * Accumulates into the context's device accumulation buffers (zeroed first). */
 int pt_render(pt_ctx *ctx, const pt_render_params *params);
 
+/* Single-process multi-GPU render: ctxs[0..n) are contexts of the SAME scene on n different devices of one node.
+ * Row tile k goes to device k % n; the devices render concurrently (one host thread each) and their resolve kernels
+ * store the rows straight into ctxs[0]'s image over NVLink peer memory.  Afterwards pt_readback(ctxs[0], ...) returns
+ * the whole image and the summed statistics (render_ms = the slowest device).  params->rank/world are ignored. */
+int pt_render_multi(pt_ctx **ctxs, int n, const pt_render_params *params);
+
 /* Same, but accumulate into caller-owned DEVICE memory (w*h*3 doubles, row-major, top row
  * first, zeroed by the call) so a host runtime (torch.distributed) can gather row tiles
  * with NCCL without a copy.  `stream` is a cudaStream_t (0 = the context's own stream). */

@@ -283,7 +283,7 @@ def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, s
 # ------------------------------------------------------------------------------ product library
 _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
-EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
+EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
            "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
@@ -298,6 +298,7 @@ def lib():
         vp = C.c_void_p
         L.pt_scene_upload.argtypes = [C.POINTER(vp), C.POINTER(SceneDesc), C.c_int]
         L.pt_render.argtypes = [vp, C.POINTER(RenderParams)]
+        L.pt_render_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(RenderParams)]
         L.pt_render_into.argtypes = [vp, C.POINTER(RenderParams), vp, vp]
         L.pt_readback.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(Stats)]
         L.pt_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -330,6 +331,15 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def render_multi(contexts, p):
+    """pt_render_multi: contexts of the same scene on different devices render one image; read it back from contexts[0]."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = lib().pt_render_multi(arr, len(contexts), C.byref(p))
+    for c in contexts:
+        c.last = p
+    contexts[0]._check(rc, "pt_render_multi")
 
 
 def specialise(scene, mode=PT_MODE_NEE_REF_RECT):

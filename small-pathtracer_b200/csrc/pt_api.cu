@@ -361,6 +361,71 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
 
 int pt_render(pt_ctx *ctx, const pt_render_params *p) { return render_common(ctx, p, nullptr, nullptr); }
 
+// Single-process multi-GPU: contexts on n devices (same scene), one host thread each; every device renders its row tiles
+// (tile k -> device k % n) and its resolve kernel stores them into ctxs[0]'s accumulation buffer over NVLink peer memory.
+int pt_render_multi(pt_ctx **ctxs, int n, const pt_render_params *p)
+{
+    if (!ctxs || n <= 0 || !p) return pt_fail(nullptr, PT_ERR_ARG, "bad argument");
+    for (int i = 0; i < n; i++) if (!ctxs[i]) return pt_fail(nullptr, PT_ERR_ARG, "null context");
+    if (n == 1) return render_common(ctxs[0], p, nullptr, nullptr);
+    pt_ctx *root = ctxs[0];
+    if (p->collect_stats || p->accumulate) return pt_fail(root, PT_ERR_ARG, "pt_render_multi does not combine with collect_stats / accumulate");
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++)
+            if (ctxs[i]->device == ctxs[j]->device) return pt_fail(root, PT_ERR_ARG, "pt_render_multi needs one context per device");
+    // the root's image: (re)allocated here so that the workers can write to it
+    PT_CUDA(root, cudaSetDevice(root->device));
+    const size_t n_acc = (size_t)p->width * p->height * 3;
+    if (p->width <= 0 || p->height <= 0) return pt_fail(root, PT_ERR_ARG, "bad image size");
+    if (root->accum_elems < n_acc) {
+        if (root->d_sum) cudaFree(root->d_sum);
+        if (root->d_sumsq) cudaFree(root->d_sumsq);
+        root->d_sum = root->d_sumsq = nullptr; root->accum_elems = 0;
+        PT_CUDA(root, cudaMalloc(&root->d_sum, n_acc * sizeof(double)));
+        PT_CUDA(root, cudaMalloc(&root->d_sumsq, n_acc * sizeof(double)));
+        root->accum_elems = n_acc;
+    }
+    for (int i = 1; i < n; i++) {           // peer access device i -> root's device
+        int can = 0;
+        PT_CUDA(root, cudaDeviceCanAccessPeer(&can, ctxs[i]->device, root->device));
+        if (!can) return pt_fail(root, PT_ERR_STATE, "no peer access between the devices");
+        PT_CUDA(root, cudaSetDevice(ctxs[i]->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return pt_fail(root, PT_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    std::vector<int> rc(n, PT_OK);
+    std::vector<std::thread> th;
+    double *target = root->d_sum;
+    for (int i = 0; i < n; i++) {
+        th.emplace_back([=, &rc] {
+            pt_render_params q = *p;
+            q.rank = i; q.world = n; q.owned_rows_only = 1;
+            if (q.tile_rows <= 0) q.tile_rows = 8;
+            rc[i] = render_common(ctxs[i], &q, target, nullptr);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rc[i] != PT_OK) return pt_fail(root, rc[i], std::string("device ") + std::to_string(ctxs[i]->device) + ": " + ctxs[i]->err);
+    // the root answers pt_readback for the whole image; its statistics are the sums over the devices
+    pt_stats tot = root->stats;
+    for (int i = 1; i < n; i++) {
+        const pt_stats &a = ctxs[i]->stats;
+        tot.paths += a.paths; tot.rays_camera += a.rays_camera; tot.rays_scatter += a.rays_scatter; tot.rays_shadow += a.rays_shadow;
+        tot.shaded_vertices += a.shaded_vertices; tot.miss_events += a.miss_events; tot.truncated += a.truncated;
+        tot.kernel_launches += a.kernel_launches; tot.queue_slots_io += a.queue_slots_io;
+        tot.iterations = std::max(tot.iterations, a.iterations);
+        tot.max_depth_seen = std::max(tot.max_depth_seen, a.max_depth_seen);
+        tot.render_ms = std::max(tot.render_ms, a.render_ms);
+    }
+    root->stats = tot;
+    root->d_sum_ext = nullptr;
+    root->last = *p;
+    root->last.rank = 0; root->last.world = 1; root->last.owned_rows_only = 0;
+    return PT_OK;
+}
+
 int pt_debug_stats(pt_ctx *ctx, pt_stats *stats)
 {
     if (!ctx || !stats) return PT_ERR_ARG;

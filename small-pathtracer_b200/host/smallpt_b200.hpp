@@ -216,18 +216,31 @@ SceneTable scene_C();     // 7 rectangles + the two commented spheres of :297-29
 SceneTable scene_synthetic(int n_spheres = 256, int n_tilted = 8, uint64_t seed = 12345);   // config C4
 SceneTable scene_by_name(const std::string &name);
 
-// Thin RAII wrapper over the C ABI.
+// Thin RAII wrapper over the C ABI.  n_gpus > 1: one context per device (0 .. n_gpus-1), row tiles rendered concurrently
+// and assembled in device 0's image over NVLink peer memory (pt_render_multi).
 class Renderer {
 public:
-    Renderer(const SceneTable &scene, const Camera &cam, int device = -1) : ctx_(nullptr)
+    Renderer(const SceneTable &scene, const Camera &cam, int device = -1, int n_gpus = 1) : ctx_(nullptr)
     {
         pt_scene s = scene.pod(cam);
-        check(pt_scene_upload(&ctx_, &s, device), "pt_scene_upload");
+        if (n_gpus <= 1) { check(pt_scene_upload(&ctx_, &s, device), "pt_scene_upload"); all_.push_back(ctx_); return; }
+        for (int d = 0; d < n_gpus; d++) {
+            pt_ctx *c = nullptr;
+            int rc = pt_scene_upload(&c, &s, d);
+            if (rc != PT_OK) { std::string msg = pt_last_error(nullptr); for (pt_ctx *x : all_) pt_destroy(x); all_.clear(); ctx_ = nullptr;
+                               throw std::runtime_error("pt_scene_upload on device " + std::to_string(d) + " failed: " + msg); }
+            all_.push_back(c);
+        }
+        ctx_ = all_[0];
     }
-    ~Renderer() { if (ctx_) pt_destroy(ctx_); }
+    ~Renderer() { for (pt_ctx *c : all_) pt_destroy(c); }
     Renderer(const Renderer &) = delete;
     Renderer &operator=(const Renderer &) = delete;
-    void render(const pt_render_params &p) { check(pt_render(ctx_, &p), "pt_render"); }
+    void render(const pt_render_params &p)
+    {
+        if (all_.size() > 1) check(pt_render_multi(all_.data(), int(all_.size()), &p), "pt_render_multi");
+        else check(pt_render(ctx_, &p), "pt_render");
+    }
     std::vector<double> readback(int w, int h, pt_stats *stats = nullptr, std::vector<double> *sumsq = nullptr)
     {
         std::vector<double> rgb(size_t(w) * h * 3);
@@ -253,6 +266,7 @@ private:
         if (rc != PT_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + pt_last_error(ctx_));
     }
     pt_ctx *ctx_;
+    std::vector<pt_ctx *> all_;
 };
 
 }  // namespace smallpt_b200

@@ -3,6 +3,7 @@
 //                             [--size WxH] [--validate] [--det-sincos] [--seed N] [--out file.ppm]
 //                             [--ppm6 file] [--pfm file] [--raw64 file] [--variance file] [--dump-scene file]
 //                             [--chunk N] [--checkpoint file] [--resume file]      progressive accumulation
+//                             [--gpus N]                                           row tiles over N GPUs of this node
 // `spp` is argv[1] as the north star asks (the reference hard-codes samps = 16 at :508).
 #include <algorithm>
 #include <chrono>
@@ -19,7 +20,7 @@ int main(int argc, char *argv[])
     int w = 512, h = 512;          // :507
     int samps = 16;                // :508
     std::string mode = "nee", scene_name = "A", out = "image.ppm", scene_file, ppm6, pfm, raw64, variance, dump_scene, checkpoint, resume;
-    int chunk = 0;
+    int chunk = 0, gpus = 1;
     bool validate = false, det = false;
     uint64_t seed = 0;
     int argi = 1;
@@ -44,6 +45,7 @@ int main(int argc, char *argv[])
         else if (a == "--variance") variance = need("--variance");
         else if (a == "--dump-scene") dump_scene = need("--dump-scene");
         else if (a == "--chunk") chunk = std::atoi(need("--chunk"));
+        else if (a == "--gpus") gpus = std::atoi(need("--gpus"));
         else if (a == "--checkpoint") checkpoint = need("--checkpoint");
         else if (a == "--resume") resume = need("--resume");
         else { std::cerr << "unknown argument " << a << "\n"; return 2; }
@@ -73,7 +75,11 @@ int main(int argc, char *argv[])
             o << scene_to_text(scene, cam_spec);
         }
         Camera cam = cam_spec.make(w, h);                                              // :521
-        Renderer r(scene, cam);
+        if (gpus > 1 && (validate || chunk > 0 || !resume.empty() || !checkpoint.empty() || !variance.empty())) {
+            std::cerr << "--gpus N combines with the plain FP32 render only\n";
+            return 2;
+        }
+        Renderer r(scene, cam, -1, gpus);
         // Progressive accumulation: the sample range [0, samps) in chunks; every chunk continues the same image (samples are
         // Philox streams keyed by their index), a checkpoint holds the per-pixel sums and the number of samples in them.
         if ((chunk > 0 || !resume.empty() || !checkpoint.empty()) && (validate || !variance.empty())) {

@@ -90,3 +90,24 @@ def test_two_processes_assemble_through_cuda_ipc(tmp_path):
         for rep in range(2):
             c.render(ptb.params(w, h, spp, mode=0, seed=9 + rep))
             assert np.array_equal(np.load(out + str(rep) + ".npy") / spp, c.readback()[0])
+
+
+def test_single_process_multi_gpu_render():
+    # pt_render_multi: one context per device, resolve kernels store into device 0's image over peer memory
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    w, h, spp = 96, 50, 16
+    sc = ptb.builtin_scene("A", w, h)
+    ctxs = [ptb.Context(sc, device=d) for d in range(n)]
+    try:
+        ctxs[0].render(ptb.params(w, h, spp, mode=0, seed=21))
+        single, st1 = ctxs[0].readback()
+        ptb.render_multi(ctxs, ptb.params(w, h, spp, mode=0, seed=21, tile_rows=4))
+        multi, stn = ctxs[0].readback()
+        assert np.array_equal(single, multi)
+        assert stn.paths == st1.paths == w * h * spp and stn.rays == st1.rays
+    finally:
+        for c in ctxs:
+            c.close()

@@ -1,8 +1,8 @@
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s32_n$N.json 2> gpurun_out/bench_s32_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s32_n$N.json | python -c "
+python -m pytest tests/test_gpu_sharding.py -m gpu -q -x > gpurun_out/pytest_gpu_s33.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu_s33.log
+./small-pathtracer_b200/smallpt 256 --size 1920x1080 --out /tmp/one.ppm
+./small-pathtracer_b200/smallpt 256 --size 1920x1080 --gpus 2 --out /tmp/two.ppm
+cmp /tmp/one.ppm /tmp/two.ppm && echo "IMAGES IDENTICAL"
+./small-pathtracer_b200/smallpt 1024 --size 3840x2160 --gpus 2 --out /tmp/c5.ppm
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_s33_n2.json 2> gpurun_out/bench_s33_n2.err; tail -1 gpurun_out/bench_s33_n2.json | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d.get('strong_scaling'))"
-done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 8 --steps 5 --warmup 3 --assembly nccl > gpurun_out/bench_s32_n8_nccl.json 2> gpurun_out/bench_s32_n8_nccl.err; tail -1 gpurun_out/bench_s32_n8_nccl.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d.get('strong_scaling'))"
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d['config']['tile_rows'], d.get('strong_scaling'))"
