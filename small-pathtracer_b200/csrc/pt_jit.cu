@@ -39,6 +39,8 @@ struct Nvrtc {
     nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *) = nullptr;
     nvrtcResult (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
     nvrtcResult (*DestroyProgram)(nvrtcProgram *) = nullptr;
+    nvrtcResult (*Version)(int *, int *) = nullptr;
+    int major = 0, minor = 0;
     bool ok = false;
     std::string why;
 };
@@ -58,7 +60,8 @@ Nvrtc &nvrtc()
         if (!n.h) { n.why = "libnvrtc not found"; return; }
 #define PT_SYM(f) *(void **)(&n.f) = dlsym(n.h, "nvrtc" #f); if (!n.f) { n.why = "nvrtc" #f " missing"; return; }
         PT_SYM(CreateProgram) PT_SYM(CompileProgram) PT_SYM(GetCUBINSize) PT_SYM(GetCUBIN)
-        PT_SYM(GetProgramLogSize) PT_SYM(GetProgramLog) PT_SYM(DestroyProgram)
+        PT_SYM(GetProgramLogSize) PT_SYM(GetProgramLog) PT_SYM(DestroyProgram) PT_SYM(Version)
+        n.Version(&n.major, &n.minor);
 #undef PT_SYM
         n.ok = true;
     });
@@ -226,6 +229,7 @@ static std::string cache_path(const std::string &spec)
     mix(spec.data(), spec.size());
     mix(PT_KERNEL_SRC, sizeof(PT_KERNEL_SRC));
     if (const char *o = std::getenv("PTB200_JIT_OPTS")) mix(o, std::strlen(o));
+    { Nvrtc &n = nvrtc(); const int v[2] = {n.major, n.minor}; mix((const char *)v, sizeof v); }   // another compiler, another file
     char b[64];
     std::snprintf(b, sizeof b, "/ptb200-%016llx.cubin", hsh);
     return dir + b;
