@@ -4,20 +4,24 @@
 // intersect()/hittingPoint() :323-335/:371-377, the per-primitive intersect()/normal() members
 // (:102-124, :145-167, :188-210, :229-253), random_scattering() :337-360 and light_sampling() :363-369.
 //
-// Organisation (one kernel launch = one bounce of every live path):
-//   * path state lives in SoA float4 queues (3 x 16 B per path: origin+pixel, direction+sample,
-//     throughput+depth/prev/E); loads and stores are 128-bit and fully coalesced; the queues are sized to
-//     stay resident in the 126 MB L2 between bounces;
-//   * the scene sits in __constant__ memory, sorted by primitive class, so the intersection loops have
-//     warp-uniform operands and no memory traffic;
-//   * k_bounce fuses extend (closest hit), shade (emission, Russian roulette, light sampling + shadow
-//     ray, BSDF sampling), REGENERATION (a lane whose path ended starts the next camera path: ray
-//     generation with uniform sub-pixel jitter) and COMPACTION (warp ballot + block prefix sum + one
-//     atomic per block) of the survivors into the output queue;
-//   * randomness is Philox4x32-10 keyed by (pixel, sample, vertex): the image does not depend on queue
-//     order, chunking or the number of GPUs;
+// This file is the HOST side: queue/accumulator management, the launch loop, resolve.  The device code lives in
+// pt_kernel.cuh (compiled here ahead of time, and by pt_jit.cu at run time with the scene's constants as immediates).
+//
+// Organisation (one kernel launch = up to 128 bounces of every path slot):
+//   * k_bounce keeps the path state in registers across bounces: extend (closest hit), shade (emission, Russian
+//     roulette, light sampling + shadow ray, BSDF sampling) and REGENERATION (a lane whose path ended takes the next
+//     camera path at once: ray generation with uniform sub-pixel jitter; path indices are reserved per warp in chunks)
+//     repeat inside the kernel; COMPACTION (warp ballot + block prefix sum + one atomic per block) of the survivors into
+//     the output queue happens once per launch and matters in the tail of a render;
+//   * between launches the survivors live in SoA float4 queues (3 x 16 B per path: origin+pixel, direction+sample,
+//     throughput+depth/prev/E); loads and stores are 128-bit and fully coalesced;
+//   * the scene sits in __constant__ memory (generic build) or in the instruction stream (specialised build), sorted
+//     by primitive class; small-sphere tables are staged in shared memory for the conservative scan;
+//   * randomness is Philox4x32-10 keyed by (pixel, sample, vertex), the jitter stream Philox2x32-10: the image does
+//     not depend on queue order, chunking, bounces per launch or the number of GPUs;
 //   * radiance is accumulated per pixel in 64-bit fixed point (2^-24) with integer atomics, which are
-//     associative: the result is bit-reproducible run to run and across shardings.
+//     associative: the result is bit-reproducible run to run and across shardings; k_resolve / k_resolve_owned turn
+//     the sums into FP64 (the latter writes only this rank's rows, possibly into another GPU's image).
 //
 // FP32 numerics: rectangles keep the reference's no-epsilon rule and its (k-o)/d, o+d*t
 // forms for the winning hit so the self-hit "leak" statistics carry over; spheres use the
