@@ -1,8 +1,7 @@
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_s34.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_s34.log
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py > gpurun_out/bench_s34_c2.json 2> gpurun_out/bench_s34_c2.err; echo "bench rc=$?"; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_s34_c2.json').read().strip().splitlines()[-1])
-print("value", d["value"], "e2e", d["e2e"]["value"], "frac", d["roofline"]["frac"], "traffic", d["roofline"]["traffic"], "c4", d["secondary"]["c4"]["value"], d["secondary"]["c4"]["roofline"]["frac"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], "launches", d["gpu_launches"], d["clocks"])
-PY
-python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-400
+for N in 8 4 2; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2957$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s35_n$N.json 2> gpurun_out/bench_s35_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s35_n$N.json | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d['config']['tile_rows'], d.get('strong_scaling'))"
+done
+./small-pathtracer_b200/smallpt 1024 --size 3840x2160 --gpus 8 --out /tmp/c5.ppm
+./small-pathtracer_b200/smallpt 1024 --size 3840x2160 --gpus 8 --out /tmp/c5.ppm
