@@ -243,9 +243,6 @@ int pt_debug_erand48(pt_ctx *ctx, const uint16_t *seeds, int n_threads, int draw
 /* Philox4x32-10 on the device: ctr = n*4 uint32, key = n*2 uint32, out = n*4 uint32. KAT entry. */
 int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out);
 
-/* Philox2x32-10 (the camera-ray jitter stream): ctr = n*2 uint32, key = n uint32, out = n*2 uint32. KAT entry. */
-int pt_debug_philox2x32(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out);
-
 /* FFMA-only microbenchmark: measured FP32 issue peak of this device in TFLOP/s
  * (FMA = 2 FLOPs), the denominator of the FP32 roofline. */
 int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);

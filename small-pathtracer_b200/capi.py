@@ -284,7 +284,7 @@ def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, s
 _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
-           "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_philox2x32", "pt_debug_ffma_peak",
+           "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_ffma_peak",
            "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
 
@@ -315,7 +315,6 @@ def lib():
         L.pt_debug_intersect.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.pt_debug_erand48.argtypes = [vp, C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.pt_debug_philox.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
-        L.pt_debug_philox2x32.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
         L.pt_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pt_set_specialisation.argtypes = [vp, C.c_int]
         L.pt_debug_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -495,15 +494,6 @@ class Context:
         u32p = C.POINTER(C.c_uint32)
         self._check(lib().pt_debug_philox(self._h, c.ctypes.data_as(u32p), k.ctypes.data_as(u32p), c.shape[0],
                                           out.ctypes.data_as(u32p)), "pt_debug_philox")
-        return out
-
-    def philox2x32(self, ctr, key):
-        c = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 2)
-        k = np.ascontiguousarray(key, dtype=np.uint32).reshape(-1)
-        out = np.empty_like(c)
-        u32p = C.POINTER(C.c_uint32)
-        self._check(lib().pt_debug_philox2x32(self._h, c.ctypes.data_as(u32p), k.ctypes.data_as(u32p), c.shape[0],
-                                              out.ctypes.data_as(u32p)), "pt_debug_philox2x32")
         return out
 
     def ffma_peak(self):

@@ -788,7 +788,6 @@ static int debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, i
 }
 
 int pt_debug_philox(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out) { return debug_philox(ctx, ctr, key, n, out, 4); }
-int pt_debug_philox2x32(pt_ctx *ctx, const uint32_t *ctr, const uint32_t *key, int n, uint32_t *out) { return debug_philox(ctx, ctr, key, n, out, 2); }
 
 int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz)
 {

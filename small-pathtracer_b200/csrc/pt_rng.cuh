@@ -1,5 +1,6 @@
 // pt_rng.cuh — Philox4x32-10 (Salmon, Moraes, Dror, Shaw; SC'11), the counter-based generator of
-// the production engine.  Stream layout: ctr = (pixel, sample, vertex, purpose), key = seed.
+// the production engine.  Stream layout: ctr = (pixel, sample, vertex, purpose), key = seed; the block of a path's
+// first vertex also supplies the sub-pixel jitter of its camera ray.
 // Replaces the reference's libc rand() jitter/light draws (src/smallpt.cpp:365-366,533-534) and the
 // per-row erand48 stream (:530) with draws that depend only on (pixel, sample, vertex): any sharding
 // of the image gives bit-identical pixels.
@@ -29,20 +30,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         k1 += PT_PHILOX_W1;
     }
     return make_uint4(c0, c1, c2, c3);
-}
-
-// Philox2x32-10: half the multiplies; the camera-ray jitter needs only two uniforms per path (:533-534).
-#define PT_PHILOX2_M 0xD256D193u
-__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k)
-{
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi = __umulhi(PT_PHILOX2_M, c0), lo = PT_PHILOX2_M * c0;
-        c0 = hi ^ k ^ c1;
-        c1 = lo;
-        k += PT_PHILOX_W0;
-    }
-    return make_uint2(c0, c1);
 }
 
 // [0,1) with 24 random bits (exact in FP32; never 1.0f)

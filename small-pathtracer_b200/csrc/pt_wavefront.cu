@@ -17,7 +17,7 @@
 //     throughput+depth/prev/E); loads and stores are 128-bit and fully coalesced;
 //   * the scene sits in __constant__ memory (generic build) or in the instruction stream (specialised build), sorted
 //     by primitive class; small-sphere tables are staged in shared memory for the conservative scan;
-//   * randomness is Philox4x32-10 keyed by (pixel, sample, vertex), the jitter stream Philox2x32-10: the image does
+//   * randomness is Philox4x32-10 keyed by (pixel, sample, vertex), one block per vertex: the image does
 //     not depend on queue order, chunking, bounces per launch or the number of GPUs;
 //   * radiance is accumulated per pixel in 64-bit fixed point (2^-24) with integer atomics, which are
 //     associative: the result is bit-reproducible run to run and across shardings; k_resolve / k_resolve_owned turn
@@ -61,14 +61,6 @@ __global__ void k_resolve_owned(const unsigned long long *__restrict__ fix, doub
     const unsigned int y = (tile * (unsigned int)world + (unsigned int)rank) * (unsigned int)tile_rows + (row_local - tile * (unsigned int)tile_rows);
     const size_t idx = ((size_t)y * (size_t)w + x) * 3 + ch;
     sum[idx] = (double)fix[idx] * PT_FIX_INV;
-}
-
-__global__ void k_philox2(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint2 r = philox2x32_10(ctr[2 * i], ctr[2 * i + 1], key[i]);
-    out[2 * i] = r.x; out[2 * i + 1] = r.y;
 }
 
 __global__ void k_philox(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
@@ -242,7 +234,6 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
         P.smp0 = (unsigned int)p->sample_offset;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
-        P.seed_jitter = (P.seed_lo ^ (P.seed_hi * 0x85EBCA6Bu)) + 0xC2B2AE35u;
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
         P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
 
@@ -332,8 +323,8 @@ int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int
 
 int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s, int width)
 {
-    if (width == 2) k_philox2<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
-    else k_philox<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
+    (void)width;
+    k_philox<<<(n + 127) / 128, 128, 0, s>>>(d_ctr, d_key, n, d_out);
     PT_CUDA(ctx, cudaGetLastError());
     return PT_OK;
 }

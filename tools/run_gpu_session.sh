@@ -1,7 +1,2 @@
-for N in 8 4 2; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2957$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s35_n$N.json 2> gpurun_out/bench_s35_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s35_n$N.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'], d['config']['tile_rows'], d.get('strong_scaling'))"
-done
-./small-pathtracer_b200/smallpt 1024 --size 3840x2160 --gpus 8 --out /tmp/c5.ppm
-./small-pathtracer_b200/smallpt 1024 --size 3840x2160 --gpus 8 --out /tmp/c5.ppm
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s36.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu_s36.log
+python tools/abtest.py > gpurun_out/abtest_s36.log 2>&1; cat gpurun_out/abtest_s36.log
