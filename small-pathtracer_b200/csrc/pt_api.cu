@@ -124,6 +124,8 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
     S.lx0 = (float)ctx->light.x0; S.lxw = (float)ctx->light.xw;
     S.lz0 = (float)ctx->light.z0; S.lzw = (float)ctx->light.zw;
     S.ly = (float)ctx->light.y; S.larea = (float)ctx->light.area;
+    if (ctx->light.id >= 0 && ctx->light.id < n)
+        for (int a = 0; a < 3; a++) { S.light_e[a] = (float)ctx->objs[ctx->light.id].e[a]; S.light_c[a] = (float)ctx->objs[ctx->light.id].c[a]; }
     // materials by code (unused slots stay zero)
     MatF32 zero;
     std::memset(&zero, 0, sizeof zero);

@@ -123,6 +123,8 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     def_i("code_obj0", S.code_obj0); def_i("light_code", S.light_code);
     def_f("lx0", S.lx0); def_f("lxw", S.lxw); def_f("lz0", S.lz0); def_f("lzw", S.lzw); def_f("ly", S.ly); def_f("larea", S.larea);
     def_f("sph_kM2", S.sph_kM2);
+    def_f("light_ex", S.light_e[0]); def_f("light_ey", S.light_e[1]); def_f("light_ez", S.light_e[2]);
+    def_f("light_cx", S.light_c[0]); def_f("light_cy", S.light_c[1]); def_f("light_cz", S.light_c[2]);
     if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates
         std::snprintf(b, sizeof b, "#define PT_J_SPH_IMM %d\nconstexpr float PT_J_SPHF[%d][4] = {\n", PT_JIT_SPH_IMM_MAX, S.n_sph4);
         h += b;

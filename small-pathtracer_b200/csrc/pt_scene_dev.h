@@ -39,6 +39,7 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     // NEE_REF_RECT light (src/smallpt.cpp:365-367,467,471)
     int   light_code;
     float lx0, lxw, lz0, lzw, ly, larea;
+    float light_e[3], light_c[3]; // emission and albedo of that light (a black-bodied light ends the path in place)
     int   n_lights;               // emissive spheres for NEE_CONE_SPHERE
     int   light_sph_code[32];
     float4 slot_a[3][PT_RECT_SLOTS];   // k, a1, a2 - a1, b1   (one 128-bit uniform load)

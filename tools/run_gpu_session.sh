@@ -1,8 +1,2 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s37.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_s37.log
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py --steps 10 > gpurun_out/bench_s37_c2.json 2> gpurun_out/bench_s37_c2.err; echo "bench rc=$?"; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_s37_c2.json').read().strip().splitlines()[-1])
-print("value", d["value"], "e2e", d["e2e"]["value"], "mrays", d["mrays_per_s"], "frac", d["roofline"]["frac"], "c4", d["secondary"]["c4"]["value"], d["secondary"]["c4"]["roofline"]["frac"], "cpu", d["cpu_baseline"]["value"])
-PY
-python tools/run_configs.py > gpurun_out/configs_s37.json 2> gpurun_out/configs_s37.log; cat gpurun_out/configs_s37.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s38.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_s38.log
+python tools/abtest.py > gpurun_out/abtest_s38.log 2>&1; cat gpurun_out/abtest_s38.log
