@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s38.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_s38.log
-python tools/abtest.py > gpurun_out/abtest_s38.log 2>&1; cat gpurun_out/abtest_s38.log
+python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_s39.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_s39.log
+python tools/abtest.py > gpurun_out/abtest_s39.log 2>&1; cat gpurun_out/abtest_s39.log
