@@ -79,6 +79,7 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
             if (o.g[0] >= PT_HUGE_RADIUS) {
                 double *h = S.huge[S.n_huge];
                 h[0] = o.g[1]; h[1] = o.g[2]; h[2] = o.g[3]; h[3] = o.g[0] * o.g[0];
+                for (int a = 0; a < 3; a++) S.hugef[S.n_huge][a] = (float)h[a];
                 code_of[i] = S.code_huge0 + S.n_huge++;
             } else {
                 S.sph[S.n_sph] = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(o.g[0] * o.g[0]));

@@ -55,6 +55,7 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     int    n_sph4;                // n_sph rounded up to a multiple of 4
     int    refl_mask;             // bit r set: some object has material r (PT_DIFF / PT_SPEC / PT_REFR)
     double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64
+    float  hugef[PT_MAX_HUGE][4]; // the same centres rounded to FP32 (for b = (c - o).d)
     float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
 };
 
