@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--assembly", default="auto", choices=["auto", "nccl"], help="N > 1: auto = peer-memory stores when CUDA IPC works, else NCCL gather")
+    ap.add_argument("--no-ffma-peak", action="store_true", help="roofline against the theoretical FP32 peak (keeps the microbenchmark out of an ncu launch list)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the extra C4 (intersection-bound) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -378,7 +379,7 @@ def main():
     # ------------------------------------------------------------------ roofline (rank 0's dominant kernel: k_bounce)
     peaks, peak_src = read_peaks()
     try:
-        ffma_tf, _ = ctx.ffma_peak()
+        ffma_tf = None if args.no_ffma_peak else ctx.ffma_peak()[0]
     except Exception:
         ffma_tf = None
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)

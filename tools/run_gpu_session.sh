@@ -1,8 +1,2 @@
-for N in 8 4 2; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2958$N bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_s46_n$N.json 2> gpurun_out/bench_s46_n$N.err; echo "bench n$N rc=$?"; tail -1 gpurun_out/bench_s46_n$N.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mrays_per_s'], d['config']['assembly'][:20], d.get('strong_scaling'))"
-done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29590 bench.py --gpus 8 --steps 5 --warmup 3 --assembly nccl > gpurun_out/bench_s46_n8_nccl.json 2> gpurun_out/bench_s46_n8_nccl.err; tail -1 gpurun_out/bench_s46_n8_nccl.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['assembly'][:20], d.get('strong_scaling'))"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_s48.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --no-ffma-peak > gpurun_out/ncu_l_s48.log 2>&1
+tail -1 gpurun_out/ncu_l_s48.log | cut -c1-300
