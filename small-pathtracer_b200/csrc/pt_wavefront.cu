@@ -214,6 +214,10 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             unsigned int chunk = 32;
             while (chunk < 256 && chunk * 2ull <= c) chunk *= 2;
             P.chunk = chunk;
+            unsigned int sh = 0;
+            while ((1ull << sh) < (unsigned long long)(cap / 32) / 2ull) sh++;     // fair share = remaining / (warps / 2)
+            if (const char *e = std::getenv("PTB200_FAIR_DELTA")) { const int dlt = std::atoi(e); sh = (unsigned int)std::max(0, (int)sh + dlt); }
+            P.fair_shift = sh;
         }
         P.total_paths = total;
         P.owned_pixels = (unsigned int)owned_pixels;
