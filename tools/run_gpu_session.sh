@@ -1,7 +1,1 @@
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_s51.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_s51.log
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py --steps 10 > gpurun_out/bench_s51_c2.json 2> gpurun_out/bench_s51_c2.err; echo "bench rc=$?"; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_s51_c2.json').read().strip().splitlines()[-1])
-print("value", d["value"], "e2e", d["e2e"]["value"], "mrays", d["mrays_per_s"], "frac", d["roofline"]["frac"], "c4", d["secondary"]["c4"]["value"], d["secondary"]["c4"]["roofline"]["frac"], "cpu", d["cpu_baseline"]["value"], "traffic", d["roofline"]["traffic"])
-PY
+python -m pytest tests/test_bench_contract.py -m gpu -q -x 2>&1 | tail -5
