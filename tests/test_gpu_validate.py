@@ -141,3 +141,23 @@ def test_edge_cases_and_errors():
             c2.render(ptb.params(4, 4, 1, mode=0))
     with pytest.raises(ptb.PtError):
         ptb.Context(ptb.Scene([ptb.sphere(-1.0, (0, 0, 0))], [], [~0], ptb.Light(), sc.camera))
+
+
+def test_gate1_full_size_c2():
+    # BASELINE.json configs[1] at FULL size: built-in scene, 512x512, 512 spp, the reference's explicit light sampling +
+    # Russian roulette.  FP64 erand48 replay on the GPU vs the CPU oracle (all host threads): per-pixel radiance within
+    # 1e-9 relative on >= 99.9 % of pixels (here: every pixel), identical ray/vertex/miss counters.
+    w = h = 512
+    spp = 512
+    sc = ptb.builtin_scene("A", w, h)
+    p = ptb.params(w, h, spp, mode=0, engine=ptb.PT_ENGINE_FP64_ERAND48, sincos=ptb.PT_SINCOS_DET)
+    with ptb.Context(sc) as c:
+        c.render(p)
+        mean, st = c.readback()
+    ptb.load_oracle().oracle_set_threads(0)
+    cl, omean, osq, ost = ptb.oracle_render(sc, p)
+    frac = match_fraction(mean, omean)
+    assert frac >= 0.999, frac
+    assert (st.paths, st.rays_shadow, st.rays_scatter, st.shaded_vertices, st.miss_events) == \
+           (ost.paths, ost.rays_shadow, ost.rays_scatter, ost.shaded_vertices, ost.miss_events)
+    assert st.paths == w * h * spp

@@ -1,1 +1,1 @@
-python -m pytest tests/test_bench_contract.py -m gpu -q -x 2>&1 | tail -5
+python -m pytest tests/test_gpu_validate.py -m gpu -q -x -k full_size --durations=3 2>&1 | tail -8
