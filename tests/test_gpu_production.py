@@ -319,3 +319,22 @@ def test_full_size_c5_sharding_properties():
     # same scene, wider aspect: compare the centre 2160x2160 crop's mean luminance loosely with the square reference view
     crop = single[:, (w - h) // 2:(w + h) // 2]
     assert abs(crop.mean() - ref.mean()) < 0.25 * ref.mean()
+
+
+def test_full_size_c4_properties():
+    # BASELINE.json configs[3] at FULL size (256 spheres + tilted planes, 1920x1080, 256 spp): the generic and the
+    # scene-specialised build (sphere table as immediates) render the bit-identical image; counters agree; no NaN.
+    w, h, spp = 1920, 1080, 256
+    sc = ptb.builtin_scene("synthetic", w, h)
+    out = []
+    with ptb.Context(sc) as c:
+        for spec in (0, 2):
+            c.set_specialisation(spec)
+            c.render(ptb.params(w, h, spp, mode=1, seed=1))
+            img, st = c.readback_view()
+            out.append((img.copy(), st.paths, st.rays, st.shaded_vertices, st.miss_events, st.specialised))
+    assert out[0][5] == 0 and out[1][5] == 1
+    assert out[0][1:5] == out[1][1:5] and out[0][1] == w * h * spp
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.isfinite(out[0][0]).all() and (out[0][0] >= 0).all()
+    assert 7.5 < out[0][2] / out[0][1] < 9.5          # rays per path of the cosine estimator on this scene (8.4)

@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_production.py -m gpu -q -x -k full_size_c5 --durations=3 2>&1 | tail -12
+python -m pytest tests -m gpu -q --durations=6 > gpurun_out/pytest_gpu_s52.log 2>&1; echo "pytest rc=$?"; tail -14 gpurun_out/pytest_gpu_s52.log
