@@ -408,7 +408,7 @@ def main():
                        "rays_per_path": rays / paths, "seed": 0,
                        "kernel": ("scene-specialised k_bounce (NVRTC build with the scene constants as immediates, compiled once during warm-up)"
                                   if stats.specialised else "generic k_bounce (scene in __constant__ memory)"),
-                       "bounces_per_launch": 128},
+                       "bounces_per_launch": 512},
             "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
             "clocks": clocks, "gpu_launches": int(launches_all),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -127,7 +127,7 @@ typedef struct pt_render_params {
     int      max_depth;       /* safety cap on path length; 0 = default (4096) */
     int      queue_capacity;  /* wavefront queue slots; 0 = default (sized to L2) */
     int      collect_stats;   /* 1 = also accumulate per-pixel sum of squares */
-    int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (128) */
+    int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (512) */
     /* Progressive / checkpointable accumulation (FP32 engine).  accumulate = 1 renders samples
      * [sample_offset, sample_offset + spp) ON TOP of what the context already holds (same image size, mode, seed and
      * sharding) instead of starting from zero.  Samples are Philox streams keyed by their index and the accumulators

@@ -7,7 +7,7 @@
 // This file is the HOST side: queue/accumulator management, the launch loop, resolve.  The device code lives in
 // pt_kernel.cuh (compiled here ahead of time, and by pt_jit.cu at run time with the scene's constants as immediates).
 //
-// Organisation (one kernel launch = up to 128 bounces of every path slot):
+// Organisation (one kernel launch = up to 512 bounces of every path slot):
 //   * k_bounce keeps the path state in registers across bounces: extend (closest hit), shade (emission, Russian
 //     roulette, light sampling + shadow ray, BSDF sampling) and REGENERATION (a lane whose path ended takes the next
 //     camera path at once: ray generation with uniform sub-pixel jitter; path indices are reserved per warp in chunks)

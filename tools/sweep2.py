@@ -6,7 +6,7 @@ if os.environ.get("PTB200_LIB"):
     ptb.capi.LIB_PATH = os.environ["PTB200_LIB"]
 bps = int(os.environ.get("PTB200_BPS", "5"))
 wave = 148 * bps * 256
-cases = {"c2": ("A", 512, 512, 512, 0), "c1x8": ("A", 512, 512, 128, 1), "c4/8": ("synthetic", 1920, 1080, 32, 1), "c5/16": ("A", 3840, 2160, 64, 0)}
+cases = {"c2": ("A", 512, 512, 512, 0), "c1x8": ("A", 512, 512, 128, 1), "c4/8": ("synthetic", 1920, 1080, 32, 1), "c5/16": ("A", 3840, 2160, 256, 0)}
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else list(cases)
 for name in only:
     scene, w, h, spp, mode = cases[name]
