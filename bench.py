@@ -383,7 +383,8 @@ def main():
     except Exception:
         ffma_tf = None
     sm_mhz = peaks.get("sm_max_mhz", 1965.0)
-    fp32_theory = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count          # 148 on B200
+    fp32_theory = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
     f_isect = scene.flops_per_ray()
     my_flops = float(stats.rays) * f_isect + float(stats.shaded_vertices) * F_SHADE[mode]     # per step, this rank
     k_ms = stats.render_ms                                                                   # CUDA events around the launches
@@ -392,7 +393,7 @@ def main():
     qbytes = 48.0 * float(stats.queue_slots_io)                       # 48 B per path record read or written through the queues
     roofline = {"bound": "fp32", "kernel": "k_bounce", "achieved": achieved_tf, "peak": ffma_tf or fp32_theory, "unit": "TFLOP/s",
                 "frac": achieved_tf / (ffma_tf or fp32_theory),
-                "peak_source": "FFMA-only microbenchmark measured in this run (pt_debug_ffma_peak)" if ffma_tf else "148 SM x 128 lanes x 2 x sm_max_mhz",
+                "peak_source": "FFMA-only microbenchmark measured in this run (pt_debug_ffma_peak)" if ffma_tf else f"{n_sm} SM x 128 lanes x 2 x sm_max_mhz",
                 "peak_theoretical": fp32_theory, "frac_of_theoretical": achieved_tf / fp32_theory,
                 "flops_per_ray": f_isect, "flops_per_bounce": F_SHADE[mode],
                 "avg_launch_ms": per_launch_ms, "launches_per_step": int(stats.iterations),
