@@ -125,6 +125,9 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     def_f("sph_kM2", S.sph_kM2);
     def_f("light_ex", S.light_e[0]); def_f("light_ey", S.light_e[1]); def_f("light_ez", S.light_e[2]);
     def_f("light_cx", S.light_c[0]); def_f("light_cy", S.light_c[1]); def_f("light_cz", S.light_c[2]);
+    // Cone sampling of many sphere lights keeps a shadow-ray loop's state live across the unrolled scan: inlined, the
+    // 64-register budget spills ~1.7 KB per thread (synthetic scene: 23 Mpaths/s); as a call, 53 Mpaths/s.
+    if (mode == PT_MODE_NEE_CONE_SPHERE && S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX && S.n_lights > 1) h += "#define PT_NOINLINE_HIT 1\n";
     if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates
         std::snprintf(b, sizeof b, "#define PT_J_SPH_IMM %d\nconstexpr float PT_J_SPHF[%d][4] = {\n", PT_JIT_SPH_IMM_MAX, S.n_sph4);
         h += b;

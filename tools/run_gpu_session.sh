@@ -1,1 +1,2 @@
-python tools/sweep_opts.py "" "-DPT_BLOCKS_PER_SM=3" "-DPT_NOINLINE_HIT" "-DPT_NOINLINE_HIT -DPT_BLOCKS_PER_SM=3" 2>&1 | tee gpurun_out/sweep_blocks_b.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/sweep_opts.py "" 2>&1 | tee gpurun_out/sweep_default.txt
