@@ -158,12 +158,13 @@ def test_full_size_c2_properties():
     assert np.isfinite(a).all() and (a >= 0).all()
 
 
-@pytest.mark.parametrize("scene,mode", [("A", 0), ("A", 1), ("B", 1), ("synthetic", 1), ("B", 3)])
+@pytest.mark.parametrize("scene,mode", [("A", 0), ("A", 1), ("B", 1), ("synthetic", 1), ("B", 3), ("synthetic", 3)])
 def test_scene_specialised_kernel_matches_the_generic_one(scene, mode):
     # the NVRTC build folds the scene's constants into the instruction stream and drops what the scene does not use,
     # but performs the same floating-point operations in the same order: same Philox streams in, the SAME image out,
     # bit for bit, with identical ray counts (every branch of every path went the same way)
-    w, h, spp = 160, 120, 64
+    # (synthetic, cone sampling of its ~25 sphere lights: the specialised build calls closest_hit instead of inlining it)
+    w, h, spp = (160, 120, 64) if (scene, mode) != ("synthetic", 3) else (160, 120, 4)
     sc = ptb.builtin_scene(scene, w, h)
     out = []
     with ptb.Context(sc) as c:

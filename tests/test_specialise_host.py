@@ -24,6 +24,15 @@ def test_specialised_source_compiles_for_sm100a(scene, mode):
     assert seconds < 60
 
 
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+def test_cone_sampling_over_a_large_sphere_table_calls_closest_hit():
+    # many sphere lights x an unrolled 200-sphere scan: inlined three times the kernel spills kilobytes per thread
+    sc = ptb.builtin_scene("synthetic", 64, 64)
+    assert "#define PT_NOINLINE_HIT 1" in ptb.specialise(sc, 3)[0]
+    assert "PT_NOINLINE_HIT" not in ptb.specialise(sc, 1)[0]
+    assert "PT_NOINLINE_HIT" not in ptb.specialise(ptb.builtin_scene("B", 64, 64), 3)[0]
+
+
 def test_header_carries_the_scene_constants():
     sc = ptb.builtin_scene("A", 64, 64)
     spec, _, _ = ptb.specialise(sc, 0)
