@@ -226,6 +226,8 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
         P.use_magic = (owned_pixels < (1ull << 24) && w < 65536 && tile < 65536) ? 1 : 0;
+        P.key_low = PT_KEY_CODE_BITS;
+        P.wrap_once = owned_pixels >= 32ull ? 1 : 0;
         P.max_depth = p->max_depth > 0 ? p->max_depth : 4096;
         if (P.max_depth > 65000) P.max_depth = 65000;
         const pt_camera &c = ctx->cam;

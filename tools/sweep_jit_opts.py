@@ -18,7 +18,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             res[name] = "%.2fms %.0fMp/s" % (best, st.paths / best * 1e-3)
     print(json.dumps(res))
 else:
-    for opts, cap in [("", 0), ("-DPT_SLOT_FMA_MOVES=1", 0), ("", 0), ("-DPT_SLOT_FMA_MOVES=1", 0)]:
+    for opts, cap in [("", 0), ("-DPT_BLOCKS_PER_SM=3", 0), ("", 0), ("-DPT_BLOCKS_PER_SM=3", 0)]:
         env = dict(os.environ, PTB200_JIT_OPTS=opts, PTB200_CAP=str(cap))
         try:
             out = subprocess.check_output([sys.executable, __file__, "child"], env=env, text=True, stderr=subprocess.STDOUT).strip().splitlines()[-1]
