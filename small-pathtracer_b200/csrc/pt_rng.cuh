@@ -32,6 +32,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// The same generator with the ten round keys (k0 + r W0, k1 + r W1) taken from a table the host filled: the key is
+// a per-render constant, so its schedule needs no instruction in the kernel.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[10][2])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(PT_PHILOX_M0, c0), lo0 = PT_PHILOX_M0 * c0;
+        uint32_t hi1 = __umulhi(PT_PHILOX_M1, c2), lo1 = PT_PHILOX_M1 * c2;
+        c0 = hi1 ^ c1 ^ rk[r][0];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[r][1];
+        c3 = lo0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // [0,1) with 24 random bits (exact in FP32; never 1.0f)
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 

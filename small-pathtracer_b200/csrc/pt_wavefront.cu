@@ -240,6 +240,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
         P.smp0 = (unsigned int)p->sample_offset;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
+        for (unsigned int r = 0; r < 10; r++) { P.philox_rk[r][0] = P.seed_lo + r * PT_PHILOX_W0; P.philox_rk[r][1] = P.seed_hi + r * PT_PHILOX_W1; }
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
         P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
 
