@@ -32,6 +32,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// round keys of a Philox key: k + r * W (host: once per render, into KParams::philox_rk)
+#ifdef __CUDACC_RTC__
+__device__
+#else
+__host__ __device__
+#endif
+inline void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t (&rk)[10][2])
+{
+    for (uint32_t r = 0; r < 10; r++) { rk[r][0] = k0 + r * PT_PHILOX_W0; rk[r][1] = k1 + r * PT_PHILOX_W1; }
+}
+
 // The same generator with the ten round keys (k0 + r W0, k1 + r W1) taken from a table the host filled: the key is
 // a per-render constant, so its schedule needs no instruction in the kernel.
 __device__ __forceinline__ uint4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[10][2])

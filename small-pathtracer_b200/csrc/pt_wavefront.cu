@@ -68,6 +68,12 @@ __global__ void k_philox(const uint32_t *__restrict__ ctr, const uint32_t *__res
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+    // the render kernels use the round-key form: it must be the same function (a mismatch spoils the output, so the
+    // known-answer test fails)
+    uint32_t rk[10][2];
+    philox_round_keys(key[2 * i], key[2 * i + 1], rk);
+    const uint4 q = philox4x32_10_rk(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], rk);
+    if (q.x != r.x || q.y != r.y || q.z != r.z || q.w != r.w) r = make_uint4(~r.x, ~r.y, ~r.z, ~r.w);
     out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 
@@ -240,7 +246,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.inv_w = 1.f / (float)w; P.inv_h = 1.f / (float)h;
         P.smp0 = (unsigned int)p->sample_offset;
         P.seed_lo = (unsigned int)p->seed; P.seed_hi = (unsigned int)(p->seed >> 32);
-        for (unsigned int r = 0; r < 10; r++) { P.philox_rk[r][0] = P.seed_lo + r * PT_PHILOX_W0; P.philox_rk[r][1] = P.seed_hi + r * PT_PHILOX_W1; }
+        philox_round_keys(P.seed_lo, P.seed_hi, P.philox_rk);
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
         P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
 
