@@ -251,8 +251,12 @@ int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
  * its compiler folds every plane constant; pt_render does the same for an uploaded scene by compiling, with NVRTC,
  * a build of the bounce kernel in which the scene's rectangle constants and primitive counts are immediates (cached
  * per scene and mode for the life of the process; ~1 s the first time, outside the timed region).
- * mode: 0 = never (generic kernel, scene in __constant__ memory), 1 = for renders of >= 2^25 paths (default; the
- * environment variable PTB200_JIT overrides the default), 2 = always.  pt_stats.specialised reports what ran. */
+ * mode: 0 = never (generic kernel, scene in __constant__ memory); 1 (default; the environment variable PTB200_JIT
+ * overrides the default) = renders of >= 2^25 paths wait for the build, smaller ones never wait: once they have
+ * spent 300 ms of GPU time (PTB200_JIT_BG_MS) in the generic kernel the build of their (scene, mode) runs on a host
+ * thread and is used once it is there; 2 = always, waiting.
+ * The two builds perform the same operations in the same order (bit-identical images), so which one ran shows only
+ * in pt_stats.specialised and in the time. */
 int pt_set_specialisation(pt_ctx *ctx, int mode);
 
 /* The context's statistics record as it stands (pt_readback needs a finished render; the debug entries only set

@@ -327,8 +327,10 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode > 0) {
         // scene-specialised kernel: built (once per scene/mode) BEFORE the timed region starts
         const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp / (unsigned long long)world;
-        // (which build runs depends on the render's size only; the two builds give bit-identical images anyway — tested)
-        if (ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS) ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0);
+        // Large renders (and jit_mode 2) wait for the build; small ones never do: their specialisation is compiled on a
+        // host thread from the second render on and used once it is there.  Which build runs cannot be seen in the
+        // image: the two perform the same operations in the same order (bit-identical, tested).
+        ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0, false, ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS);
     }
     PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, p->collect_stats ? ctx->d_sumsq : nullptr, s)
@@ -345,6 +347,8 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
     st.shaded_vertices = ds.shaded; st.max_depth_seen = ds.max_depth_seen;
     st.specialised = ctx->jit ? 1u : 0u;
+    if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode == 1 && !ctx->jit)
+        pt_jit_account(ctx, p->mode, p->collect_stats != 0, ms);      // small render, generic kernel: counts towards its background build
     if (p->engine == PT_ENGINE_FP64_ERAND48) {
         st.paths = ds.paths; st.rays_camera = ds.rays_camera; st.rays_scatter = ds.rays_scatter;
     } else {

@@ -30,11 +30,12 @@ struct PtStageLane {                  // one read-back pipeline: its own stream,
     double *h_stage = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
 };
+#define PT_JIT_BACKGROUND_AFTER_MS 300.0   /* jit_mode 1, small renders: GPU time in the generic kernel before the background build starts */
 #ifndef PT_JIT_SPH_IMM_MAX
 #define PT_JIT_SPH_IMM_MAX 256          /* specialised build: sphere scan tables up to this size become immediates */
 #endif
 #define PT_STAGE_ELEMS ((size_t)1 << 17)   /* 1 MB staging blocks */
-#define PT_JIT_MIN_PATHS (1ull << 25)   /* jit_mode 1: renders at least this big use the specialised build (NVRTC ~0.5 s once, or the disk cache) */
+#define PT_JIT_MIN_PATHS (1ull << 25)   /* jit_mode 1: renders at least this big WAIT for the specialised build (NVRTC ~0.5 s once, or the disk cache); smaller ones get it in the background from their second render on */
 
 struct pt_ctx {
     int device = 0;
@@ -100,7 +101,8 @@ struct PtJitKernel {
 };
 std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false);
 int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
-PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false);
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false, bool wait = true);
+void pt_jit_account(pt_ctx *ctx, int mode, bool stats, double ms);
 int pt_jit_build(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds, bool *from_disk);
 #define PT_CUDA(ctx, call)                                                                      \
     do {                                                                                        \

@@ -18,7 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <set>
 
 #include <sys/stat.h>
@@ -82,6 +84,39 @@ unsigned int float_bits(float v) { unsigned int u; std::memcpy(&u, &v, 4); retur
 
 std::mutex g_mu;
 std::map<std::string, PtJitKernel *> g_cache;       // key = specialisation header (contains mode and stats flag)
+
+// A build running on its own host thread (NVRTC or the disk cache: no CUDA call — the module is loaded by the
+// thread that asks for the kernel).  Small renders use it: they go on with the generic kernel meanwhile.
+struct PendingBuild {
+    std::thread th;
+    std::atomic<bool> done{false};
+    int rc = PT_ERR_STATE;
+    std::vector<char> cubin;
+    std::string log;
+    double secs = 0;
+    bool from_disk = false;
+};
+struct PendingSet {
+    std::map<std::string, PendingBuild *> m;
+    ~PendingSet() { for (auto &kv : m) { if (kv.second->th.joinable()) kv.second->th.join(); delete kv.second; } }   // process exit
+};
+PendingSet g_pending;
+std::map<std::string, double> g_spent_ms;           // GPU time small renders of a specialisation spent in the generic kernel
+bool g_exit_hook = false;
+
+// Process exit with a build in flight: wait for it BEFORE libnvrtc's own static destructors run (handlers run in
+// reverse order of registration, and this one is registered after libnvrtc was loaded).
+void join_pending_at_exit()
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : g_pending.m) if (kv.second->th.joinable()) kv.second->th.join();
+}
+
+double background_after_ms()
+{
+    if (const char *e = std::getenv("PTB200_JIT_BG_MS")) return std::atof(e);
+    return PT_JIT_BACKGROUND_AFTER_MS;
+}
 
 }  // namespace
 
@@ -276,20 +311,11 @@ int pt_jit_build(const std::string &spec, std::vector<char> &cubin, std::string 
     return rc;
 }
 
-// The specialised kernel for the context's current scene, or nullptr (generic kernel) when JIT is off/unavailable.
-PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
+// Load a built cubin into the calling thread's CUDA context.
+static PtJitKernel *load_module(pt_ctx *ctx, int mode, bool with_intersect, int rc, std::vector<char> &cubin, std::string &log, double secs, bool from_disk)
 {
-    if (!ctx->fp32_ok) return nullptr;
-    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats, with_intersect);
-    std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_cache.find(spec);
-    if (it != g_cache.end()) return it->second;          // may be nullptr: a failed build is not retried
     PtJitKernel *jk = nullptr;
-    std::vector<char> cubin;
-    std::string log;
-    double secs = 0;
-    bool from_disk = false;
-    if (pt_jit_build(spec, cubin, log, &secs, &from_disk) == PT_OK) {
+    if (rc == PT_OK) {
         jk = new PtJitKernel();
         jk->compile_seconds = secs;
         cudaError_t e = cudaLibraryLoadData(&jk->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -308,6 +334,59 @@ PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect)
     } else if (std::getenv("PTB200_JIT_VERBOSE")) {
         std::fprintf(stderr, "[ptb200] scene-specialised k_bounce (mode %d) %s in %.2f s\n", mode, from_disk ? "loaded from the disk cache" : "compiled", secs);
     }
-    g_cache[spec] = jk;
     return jk;
+}
+
+// The specialised kernel for the context's current scene, or nullptr (generic kernel) when JIT is off/unavailable.
+// wait = true: build now if need be (large renders: the 0.5 s pay off at once).  wait = false (small renders): never
+// block — the SECOND request for a specialisation starts its build on a host thread, later requests pick the kernel up
+// once it is there, and until then the caller renders with the generic kernel (same image, bit for bit).
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect, bool wait)
+{
+    if (!ctx->fp32_ok) return nullptr;
+    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats, with_intersect);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_cache.find(spec);
+    if (it != g_cache.end()) return it->second;          // may be nullptr: a failed build is not retried
+    auto pit = g_pending.m.find(spec);
+    if (pit == g_pending.m.end()) {
+        if (wait) {
+            std::vector<char> cubin;
+            std::string log;
+            double secs = 0;
+            bool from_disk = false;
+            const int rc = pt_jit_build(spec, cubin, log, &secs, &from_disk);
+            return g_cache[spec] = load_module(ctx, mode, with_intersect, rc, cubin, log, secs, from_disk);
+        }
+        // buy after renting for the price: the build starts once the small renders of this specialisation have spent
+        // about a compilation's worth of GPU time in the generic kernel (a process that renders once never compiles,
+        // and none waits at exit for a build longer than it has been rendering)
+        if (g_spent_ms[spec] < background_after_ms()) return nullptr;
+        if (!nvrtc().ok) { ctx->jit_note = "generic kernel (" + nvrtc().why + ")"; return g_cache[spec] = nullptr; }
+        if (!g_exit_hook) { g_exit_hook = true; std::atexit(join_pending_at_exit); }
+        PendingBuild *pb = new PendingBuild();
+        g_pending.m[spec] = pb;
+        pb->th = std::thread([pb, spec]() {
+            pb->rc = pt_jit_build(spec, pb->cubin, pb->log, &pb->secs, &pb->from_disk);
+            pb->done.store(true, std::memory_order_release);
+        });
+        return nullptr;
+    }
+    PendingBuild *pb = pit->second;
+    if (!wait && !pb->done.load(std::memory_order_acquire)) return nullptr;
+    pb->th.join();
+    PtJitKernel *jk = load_module(ctx, mode, with_intersect, pb->rc, pb->cubin, pb->log, pb->secs, pb->from_disk);
+    g_pending.m.erase(pit);
+    delete pb;
+    g_spent_ms.erase(spec);
+    return g_cache[spec] = jk;
+}
+
+// A small render of (scene, mode) ran the generic kernel for `ms`: counts towards starting its background build.
+void pt_jit_account(pt_ctx *ctx, int mode, bool stats, double ms)
+{
+    if (!ctx->fp32_ok) return;
+    const std::string spec = pt_jit_spec(*ctx->h_scene32, mode, stats, false);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_cache.find(spec) == g_cache.end() && g_pending.m.find(spec) == g_pending.m.end()) g_spent_ms[spec] += ms;
 }

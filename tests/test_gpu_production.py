@@ -210,19 +210,48 @@ def test_readback_view_equals_readback():
         assert np.array_equal(c.readback()[0], c.readback_view()[0])
 
 
-def test_default_policy_depends_on_the_render_size_only():
-    # pt_set_specialisation mode 1 (default): renders of >= 2^25 paths use the NVRTC build, smaller ones the generic
-    # kernel; never history-dependent (the same call must give the same image)
+def test_default_policy_large_renders_wait_small_ones_never_do():
+    # pt_set_specialisation mode 1 (default): a render of >= 2^25 paths waits for the NVRTC build of its (scene, mode);
+    # a smaller one never waits — it takes the specialised kernel if it exists, else the generic one — and the image
+    # cannot tell which ran (the same call must give the same image)
     w = h = 512
-    with ptb.Context(ptb.builtin_scene("A", w, h)) as c:
+    with ptb.Context(_shelf_scene(2, w, h)) as c:             # a scene no other test specialises (the cache is per process)
         c.set_specialisation(1)
         flags, imgs = [], []
         for spp in (64, 128, 64, 128):                        # 2^24 and 2^25 paths, twice
-            c.render(ptb.params(w, h, spp, mode=1))
+            c.render(ptb.params(w, h, spp, mode=1, seed=5))
             flags.append(c.stats().specialised)
             imgs.append(c.readback()[0])
-        assert flags == [0, 1, 0, 1], flags
+        assert flags == [0, 1, 1, 1], flags                   # the third render finds the kernel the second one built
         assert np.array_equal(imgs[0], imgs[2]) and np.array_equal(imgs[1], imgs[3])
+
+
+def test_small_renders_get_their_specialisation_in_the_background(monkeypatch):
+    # small renders never wait for a compilation: once they have spent PTB200_JIT_BG_MS (default 300 ms) of GPU time in
+    # the generic kernel the build starts on a host thread while the generic kernel keeps rendering; once it is there it
+    # is used, and nothing changes in the image
+    import time
+    monkeypatch.setenv("PTB200_JIT_BG_MS", "3")
+    w, h, spp = 512, 512, 8
+    sc = _shelf_scene(3, w, h)                                # a scene no other test specialises (the cache is per process)
+    with ptb.Context(sc) as c:
+        c.set_specialisation(1)
+        c.render(ptb.params(w, h, spp, mode=2, seed=3))
+        first, st = c.readback()
+        assert st.specialised == 0
+        waited, st = 0.0, None
+        deadline = time.time() + 60
+        while time.time() < deadline:
+            t0 = time.time()
+            c.render(ptb.params(w, h, spp, mode=2, seed=3))
+            waited = max(waited, time.time() - t0)
+            img, st = c.readback()
+            assert np.array_equal(img, first)
+            if st.specialised:
+                break
+            time.sleep(0.02)
+        assert st.specialised == 1, "the background build never arrived"
+        assert waited < 0.2, "a small render blocked on the compilation (%.2f s)" % waited
 
 
 def _shelf_scene(n_shelves, w, h):
