@@ -22,7 +22,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             res[name] = "%.2f ms %.0f Mp/s%s" % (best, st.paths / best * 1e-3, " [spec]" if st.specialised else "")
     print(json.dumps(res))
 else:
-    libs = [("", "0"), ("", "2")] + [(os.path.join(ROOT, "expt", f), os.environ.get("ABTEST_EXPT_SPEC", "2")) for f in sorted(os.listdir(os.path.join(ROOT, "expt"))) if f.endswith(".so")]
+    libs = [("", "0"), ("", "2")] + [(os.path.join(ROOT, "expt", f), os.environ.get("ABTEST_EXPT_SPEC", "2")) for f in (sorted(os.listdir(os.path.join(ROOT, "expt"))) if os.path.isdir(os.path.join(ROOT, "expt")) else []) if f.endswith(".so")]
     for lib, spec in libs:
         env = dict(os.environ, PTB200_LIB=lib, PTB200_SPEC=spec)
         out = subprocess.check_output([sys.executable, __file__, "child"], env=env, text=True).strip().splitlines()[-1]
