@@ -254,6 +254,37 @@ def test_small_renders_get_their_specialisation_in_the_background(monkeypatch):
         assert waited < 0.3, "a small render blocked on the compilation (%.2f s)" % waited
 
 
+@pytest.mark.parametrize("spec", [0, 2], ids=["generic", "specialised"])
+def test_every_pixel_gets_exactly_spp_samples(spec):
+    # regeneration hands out (sample, pixel) pairs from per-warp chunks, with refills, wraps into the next sample, guided
+    # chunk sizes near the end and row-tile arithmetic for sharded renders: the pairs must be each pixel x each sample,
+    # once.  Scene: one emissive, black-bodied wall filling the view => every path returns exactly 1, so a pixel's mean
+    # is exactly 1.0 if and only if it received exactly spp samples (64-bit fixed-point sums are exact).
+    from small_pathtracer_b200 import dist as pdist
+    for w, h, spp in ((1, 1, 5), (7, 3, 33), (33, 17, 13), (100, 37, 257), (640, 360, 3), (31, 1, 64)):
+        base = ptb.builtin_scene("A", w, h)
+        wall = ptb.rect(ptb.PT_PLANE_XY, -1e4, 1e4, -1e4, 1e4, 0.0, e=(1, 1, 1), c=(0, 0, 0))
+        sc = ptb.Scene([], [wall], [0], base.light, base.camera)
+        with ptb.Context(sc) as c:
+            c.set_specialisation(spec)
+            for kw in ({}, {"queue_capacity": 8192, "bounces_per_launch": 2}):
+                c.render(ptb.params(w, h, spp, mode=1, seed=4, **kw))
+                img, st = c.readback()
+                assert st.paths == w * h * spp
+                assert np.all(img == 1.0), (w, h, spp, kw, float(img.min()), float(img.max()))
+            for world, tile in ((3, 4), (2, 1)):
+                seen = np.zeros(h, dtype=int)
+                for r in range(world):
+                    c.render(ptb.params(w, h, spp, mode=1, seed=4, tile_rows=tile, rank=r, world=world))
+                    img, st = c.readback()
+                    rows = np.asarray(pdist.owned_rows(h, tile, r, world), dtype=int)
+                    assert st.paths == len(rows) * w * spp
+                    if len(rows):
+                        assert np.all(img[rows] == 1.0), (w, h, spp, world, r)
+                    seen[rows] += 1
+                assert np.all(seen == 1)
+
+
 def _shelf_scene(n_shelves, w, h):
     """The built-in room plus a stack of thin horizontal shelves: more rectangles of one axis class than the 16 unrolled
     slots hold, so the overflow loop of closest_hit is exercised (objects in id order: the 17 of scene A, then shelves)."""

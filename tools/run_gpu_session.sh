@@ -1,3 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29594 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/bench_v9_n4.json 2> gpurun_out/bench_v9_n4.err; echo "bench n4 rc=$?"; tail -1 gpurun_out/bench_v9_n4.json | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['mrays_per_s'], d['config']['assembly'][:20], d.get('strong_scaling'))"
+timeout 120 python -m pytest tests/test_gpu_production.py -m gpu -x -q -k "exactly_spp" 2>&1 | tail -8
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
