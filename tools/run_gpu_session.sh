@@ -1,2 +1,1 @@
-timeout 120 python -m pytest tests/test_gpu_production.py -m gpu -x -q -k "exactly_spp" 2>&1 | tail -8
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/run_configs.py > gpurun_out/configs_v7.log 2>&1; echo "configs rc=$?"; tail -10 gpurun_out/configs_v7.log | cut -c1-200
