@@ -1,1 +1,4 @@
-python tools/run_configs.py > gpurun_out/configs_v7.log 2>&1; echo "configs rc=$?"; tail -10 gpurun_out/configs_v7.log | cut -c1-200
+# scratch script for `gpurun -- bash tools/run_gpu_session.sh`: the round-end checks on one B200
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench.json | cut -c1-300
