@@ -285,6 +285,23 @@ def test_every_pixel_gets_exactly_spp_samples(spec):
                 assert np.all(seen == 1)
 
 
+@pytest.mark.parametrize("engine", [0, 1], ids=["fp32-philox", "fp64-erand48"])
+def test_reference_fixture_statistics_scene_B(engine):
+    # the reference's own saved renders (512x512 P3 files) pin image means in 8-bit gamma space.
+    # image2_32pps_importancesampl.ppm (scene B, cosine, 32 spp): mean RGB (131.3, 132.8, 109.5);
+    # image_32pps_totalrandom.ppm (scene B, uniform hemisphere with weight 1, 32 spp): (102.6, 104.0, 84.8).
+    # Both GPU engines, through the reference's own output formula: clamp the per-pixel mean, toInt (:314-321, :538).
+    w = h = 512
+    sc = ptb.builtin_scene("B", w, h)
+    with ptb.Context(sc) as c:
+        for mode, want in ((1, (131.3, 132.8, 109.5)), (2, (102.6, 104.0, 84.8))):
+            c.render(ptb.params(w, h, 32, mode=mode, engine=engine, seed=2))
+            mean, _ = c.readback()
+            ints = np.floor(np.clip(mean, 0.0, 1.0) ** (1 / 2.2) * 255 + .5)
+            got = ints.reshape(-1, 3).mean(axis=0)
+            assert np.all(np.abs(got - np.array(want)) < 0.75), (engine, mode, got)
+
+
 def _shelf_scene(n_shelves, w, h):
     """The built-in room plus a stack of thin horizontal shelves: more rectangles of one axis class than the 16 unrolled
     slots hold, so the overflow loop of closest_hit is exercised (objects in id order: the 17 of scene A, then shelves)."""
