@@ -138,10 +138,11 @@ def cpu_reference(workload, budget_s, threads=0):
 
     def run_port(s):
         from _pkg import ptb
-        L = ptb.load_oracle()
+        from oracle import pyoracle as orc      # the CPU checker: cpu_baseline / --impl reference only
+        L = orc.load_oracle()
         L.oracle_set_threads(threads)
         sc = ptb.builtin_scene(scene, w, h)
-        st = ptb.oracle_render(sc, ptb.params(w, h, s, mode=mode, engine=1))[3]
+        st = orc.oracle_render(sc, ptb.params(w, h, s, mode=mode, engine=1))[3]
         return {"paths": float(st.paths), "render_ms": st.render_ms, "threads": st.threads}
 
     kind = "reference" if (os.path.exists(ref_bin) and scene_arg) else "port"

@@ -4,12 +4,18 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <thread>
 
 #include "pt_internal.h"
 
 static thread_local std::string g_last_error;   // for failures before a context exists
+
+// The FP32 engine's scene image `c_scene` is ONE __constant__ symbol per device (and one per cached specialised module):
+// contexts that share a device take turns from the upload of the symbol to the end of the render that reads it.
+static std::mutex g_dev_mutex[64];
+static std::mutex &dev_mutex(int device) { return g_dev_mutex[(unsigned)device % 64u]; }
 
 int pt_fail(pt_ctx *ctx, int code, const std::string &msg)
 {
@@ -205,8 +211,7 @@ static int upload_tables(pt_ctx *ctx)
         const int nc = (int)mats.size();
         if (ctx->n_codes_alloc < nc) {
             if (ctx->d_mats) cudaFree(ctx->d_mats);
-    if (ctx->d_sphf) cudaFree(ctx->d_sphf);
-            ctx->d_mats = nullptr; ctx->n_codes_alloc = 0;
+            ctx->d_mats = nullptr; ctx->n_codes_alloc = 0;     // d_sphf has a fixed size and is never re-allocated
             PT_CUDA(ctx, cudaMalloc(&ctx->d_mats, sizeof(MatF32) * nc));
             ctx->n_codes_alloc = nc;
         }
@@ -300,6 +305,9 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (p->engine != PT_ENGINE_FP32_PHILOX && p->engine != PT_ENGINE_FP64_ERAND48) return pt_fail(ctx, PT_ERR_ARG, "bad engine");
     const int world = p->world > 0 ? p->world : 1;
     if (p->rank < 0 || p->rank >= world) return pt_fail(ctx, PT_ERR_ARG, "rank must be in [0, world)");
+    // owned_rows_only writes ONLY this rank's rows of a (possibly shared) image; the statistics path resolves whole images
+    if (p->owned_rows_only && p->collect_stats)
+        return pt_fail(ctx, PT_ERR_ARG, "owned_rows_only does not combine with collect_stats (the per-pixel variance is resolved for the whole image)");
     if (p->mode == PT_MODE_NEE_REF_RECT && (ctx->light.id < 0 || ctx->light.id >= (int)ctx->objs.size()))
         return pt_fail(ctx, PT_ERR_ARG, "PT_MODE_NEE_REF_RECT needs pt_scene.light.id to name a scene object");
     PT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -332,6 +340,8 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
         // image: the two perform the same operations in the same order (bit-identical, tested).
         ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0, false, ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS);
     }
+    std::unique_lock<std::mutex> scene_lock(dev_mutex(ctx->device), std::defer_lock);
+    if (p->engine == PT_ENGINE_FP32_PHILOX) scene_lock.lock();      // released on return, i.e. after the stream synchronised
     PT_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     int rc = p->engine == PT_ENGINE_FP64_ERAND48 ? pt_fp64_render(ctx, p, d_sum, p->collect_stats ? ctx->d_sumsq : nullptr, s)
                                                  : pt_fp32_render(ctx, p, d_sum, ctx->d_sumsq, s);
@@ -610,8 +620,7 @@ int pt_readback(pt_ctx *ctx, double *rgb_mean, double *rgb_sumsq, pt_stats *stat
         if (p.spp > 0) {
             if (ctx->mean_elems < n) {
                 if (ctx->d_mean) cudaFree(ctx->d_mean);
-    if (ctx->h_view) cudaFreeHost(ctx->h_view);
-                ctx->d_mean = nullptr; ctx->mean_elems = 0;
+                ctx->d_mean = nullptr; ctx->mean_elems = 0;     // h_view (pt_readback_view) is independent of d_mean
                 PT_CUDA(ctx, cudaMalloc(&ctx->d_mean, n * sizeof(double)));
                 ctx->mean_elems = n;
             }
@@ -742,6 +751,7 @@ int pt_debug_intersect(pt_ctx *ctx, const double *rays_od, int n, int precision,
     PT_CUDA(ctx, cudaMalloc(&d_t, sizeof(double) * (size_t)n));
     PT_CUDA(ctx, cudaMalloc(&d_id, sizeof(int) * (size_t)n));
     int rc = PT_OK;
+    std::lock_guard<std::mutex> scene_lock(dev_mutex(ctx->device));
     cudaError_t e = cudaMemcpyAsync(d_r, rays_od, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
         rc = precision == 64 ? pt_fp64_intersect(ctx, d_r, n, d_t, d_id, ctx->stream) : pt_fp32_intersect(ctx, d_r, n, d_t, d_id, ctx->stream);
@@ -817,6 +827,7 @@ void pt_destroy(pt_ctx *ctx)
     if (ctx->d_sum) cudaFree(ctx->d_sum);
     if (ctx->d_sumsq) cudaFree(ctx->d_sumsq);
     if (ctx->d_mean) cudaFree(ctx->d_mean);
+    if (ctx->h_view) cudaFreeHost(ctx->h_view);
     if (ctx->ev_rb) cudaEventDestroy(ctx->ev_rb);
     for (int l = 0; l < PT_STAGE_LANES; l++) {
         PtStageLane &L = ctx->lane[l];

@@ -77,32 +77,39 @@ class SharedImage:
     synchronisation is one barrier after the renders.  Falls back (raises) where CUDA IPC is not available; callers then
     use `gather_rows`."""
 
-    def __init__(self, ctx, height, width, rank, world, dst=0, group=None):
+    def __init__(self, ctx, height, width, rank, world, dst=0, group=None, buffers=2):
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world, self.dst, self.group = ctx, rank, world, dst, group
         self.shape = (height, width, 3)
         nbytes = height * width * 3 * 8
-        self.ptr = None
+        # Two images, used alternately: after the barrier of render k the other ranks may already be storing render k+1
+        # (into the OTHER image) while dst still reads image k; nobody can reach render k+2 before dst has entered the
+        # barrier of render k+1, i.e. after it has let go of image k.  One image would be a write-after-read hazard.
+        self.n_buf = max(1, int(buffers))
+        self.ptrs = [None] * self.n_buf
         self.opened = False
+        self.turn = 0
         err = 0
-        handle = bytearray(64)
+        handles = bytearray(64 * self.n_buf)
         if rank == dst:
             try:
-                self.ptr = ctx.device_alloc(nbytes)
-                handle = bytearray(ctx.ipc_export(self.ptr))
+                for b in range(self.n_buf):
+                    self.ptrs[b] = ctx.device_alloc(nbytes)
+                    handles[64 * b:64 * b + 64] = ctx.ipc_export(self.ptrs[b])
             except Exception:               # noqa: BLE001
                 err = 1
         if world > 1:
-            # the 64-byte handle travels as a CPU tensor over whatever backend the group has (NCCL needs device tensors)
+            # the 64-byte handles travel as a tensor over whatever backend the group has (NCCL needs device tensors)
             dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-            t = torch.tensor(list(handle) + [err], dtype=torch.uint8, device=dev)
+            t = torch.tensor(list(handles) + [err], dtype=torch.uint8, device=dev)
             dist.broadcast(t, src=dst, group=group)
             t = t.cpu()
-            err = int(t[64])
+            err = int(t[64 * self.n_buf])
             if rank != dst and not err:
                 try:
-                    self.ptr = ctx.ipc_open(bytes(t[:64].tolist()))
+                    for b in range(self.n_buf):
+                        self.ptrs[b] = ctx.ipc_open(bytes(t[64 * b:64 * b + 64].tolist()))
                     self.opened = True
                 except Exception:           # noqa: BLE001
                     err = 1
@@ -112,28 +119,37 @@ class SharedImage:
         if err:
             self.close()
             raise RuntimeError("CUDA IPC is not available between these processes")
-        self.tensor = torch.as_tensor(_CudaArray(self.ptr, self.shape, owner=self), device=torch.device("cuda", torch.cuda.current_device())) if rank == dst else None
+        cur = torch.device("cuda", torch.cuda.current_device())
+        self.tensors = [torch.as_tensor(_CudaArray(p, self.shape, owner=self), device=cur) for p in self.ptrs] if rank == dst else None
 
-    def render(self, params, stream=0):
-        """Every rank renders its row tiles into the shared image; returns the assembled tensor (per-pixel sums) on dst."""
+    @property
+    def ptr(self):
+        return self.ptrs[self.turn]
+
+    def render(self, params, stream=0, barrier=True):
+        """Every rank renders its row tiles into the shared image of this turn; returns the assembled tensor (per-pixel
+        sums) on dst.  The tensor stays valid until the render after the next one (see __init__)."""
         import torch.distributed as dist
+        self.turn = (self.turn + 1) % self.n_buf
         params.owned_rows_only = 1
         try:
-            self.ctx.render_into(params, self.ptr, stream)       # synchronous on return: this rank's stores have landed
+            self.ctx.render_into(params, self.ptrs[self.turn], stream)       # synchronous on return: this rank's stores have landed
         finally:
             params.owned_rows_only = 0
-        if self.world > 1:
+        if self.world > 1 and barrier:
             dist.barrier(group=self.group)
-        return self.tensor
+        return self.tensors[self.turn] if self.tensors is not None else None
 
     def close(self):
-        if self.ptr is None:
-            return
         try:
-            if self.opened:
-                self.ctx.ipc_close(self.ptr)
-            elif self.rank == self.dst:
-                self.tensor = None
-                self.ctx.device_free(self.ptr)
+            for b, p in enumerate(self.ptrs):
+                if p is None:
+                    continue
+                if self.opened:
+                    self.ctx.ipc_close(p)
+                elif self.rank == self.dst:
+                    self.tensors = None
+                    self.ctx.device_free(p)
+                self.ptrs[b] = None
         finally:
-            self.ptr = None
+            self.ptrs = [None] * self.n_buf

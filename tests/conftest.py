@@ -12,6 +12,7 @@ if ROOT not in sys.path:
 os.environ.setdefault("PTB200_CACHE_DIR", "off")
 
 from _pkg import ptb  # noqa: E402
+from oracle import pyoracle as orc  # noqa: E402  (the CPU checker's loader: test infrastructure, not part of the product package)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 

@@ -143,13 +143,14 @@ def ref_units():
 
 def converged():
     from _pkg import ptb
+    from oracle import pyoracle as orc
     w = h = 128
     spp = 4096
     for scene in "AB":
         sc = ptb.builtin_scene(scene, w, h)
         for mode, name in ((0, "nee"), (1, "cos"), (2, "uni")):
             p = ptb.params(w, h, spp, mode=mode, engine=1)
-            cl, mean, sq, st = ptb.oracle_render(sc, p)
+            cl, mean, sq, st = orc.oracle_render(sc, p)
             np.savez_compressed(os.path.join(HERE, f"converged_{scene}_{name}.npz"), mean=mean.astype(np.float32),
                                 sumsq=sq.astype(np.float32), spp=np.array(spp), rays_per_path=np.array(st.rays / st.paths),
                                 miss_per_path=np.array(st.miss_events / st.paths))

@@ -24,16 +24,35 @@ def test_header_symbols_are_exported():
     assert sorted(ptb.EXPORTS) == declared
 
 
-def test_struct_layouts_match_header():
-    # sizes the C compiler gives the header's PODs (computed by a tiny C program at build time would be
-    # circular; these are the natural-alignment sizes of the declarations)
-    assert C.sizeof(ptb.Vec3) == 24
-    assert C.sizeof(ptb.Sphere) == 8 + 72 + 8
-    assert C.sizeof(ptb.Plane) == 8 + 40 + 96 + 16 + 48
-    assert C.sizeof(ptb.Camera) == 96
-    assert C.sizeof(ptb.Light) == 8 + 48
-    assert C.sizeof(ptb.RenderParams) == 24 + 8 + 16 + 16 + 8 + 8
-    assert C.sizeof(ptb.Stats) == 72 + 8 + 16 + 8
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every POD, as the C compiler sees include/ptb200.h, against the ctypes mirrors."""
+    import subprocess
+    pairs = {"pt_vec3": ptb.Vec3, "pt_sphere": ptb.Sphere, "pt_plane": ptb.Plane, "pt_camera": ptb.Camera, "pt_light": ptb.Light,
+             "pt_scene": ptb.SceneDesc, "pt_render_params": ptb.RenderParams, "pt_stats": ptb.Stats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ptb200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        c, f, v = ln.split()
+        got[(c, f)] = int(v)
+    for cname, cls in pairs.items():
+        assert got[(cname, "sizeof")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    # every field the header declares has a mirror (same count: a field added on one side only fails here)
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ptb200.h")).read(), flags=re.S)
+    for cname, cls in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
+        n_decl = sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
+        assert n_decl == len(cls._fields_), (cname, n_decl, len(cls._fields_))
 
 
 def test_version_string():

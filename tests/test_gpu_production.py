@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ptb, GOLDEN
+from conftest import ptb, orc, GOLDEN
 
 pytestmark = pytest.mark.gpu
 MODE = {"nee": 0, "cos": 1, "uni": 2}
@@ -130,7 +130,7 @@ def test_synthetic_scene_matches_oracle_statistics():
         c.render(ptb.params(w, h, 2048, mode=1, seed=5, collect_stats=1))
         mean, sq, st = c.readback(True)
     po = ptb.params(w, h, 1024, mode=1, engine=1)
-    cl, omean, osq, ost = ptb.oracle_render(sc, po)
+    cl, omean, osq, ost = orc.oracle_render(sc, po)
     z, se = z_scores(mean, sq, 2048, omean, osq, 1024)
     informative = se > 1e-9
     frac = ((np.abs(z) > 3) & informative).sum() / informative.sum()
@@ -353,7 +353,7 @@ def test_overflow_rectangles_generic_and_specialised():
     sc = _shelf_scene(24, w, h)
     from conftest import room_rays
     rays = room_rays(100000, 3, f32_exact=True, margin=2.0)
-    t_o, id_o = ptb.oracle_intersect(sc, rays)
+    t_o, id_o = orc.oracle_intersect(sc, rays)
     assert (id_o >= 17).mean() > 0.01                           # the shelves are hit
     imgs = []
     with ptb.Context(sc) as c:
@@ -416,3 +416,44 @@ def test_full_size_c4_properties():
     assert np.array_equal(out[0][0], out[1][0])
     assert np.isfinite(out[0][0]).all() and (out[0][0] >= 0).all()
     assert 7.5 < out[0][2] / out[0][1] < 9.5          # rays per path of the cosine estimator on this scene (8.4)
+
+
+def test_scene_replacement_grows_tables_safely():
+    # pt_scene_upload on an existing context, from 17 rectangles to the 256-sphere scene (the material table has to
+    # grow; the sphere scan table must survive): identical image to a fresh context, and back again
+    w, h, spp = 64, 48, 16
+    a, syn = ptb.builtin_scene("A", w, h), ptb.builtin_scene("synthetic", w, h)
+    p = ptb.params(w, h, spp, mode=1, seed=11)
+    with ptb.Context(syn) as fresh:
+        fresh.render(p)
+        want_syn = fresh.readback()[0].copy()
+    with ptb.Context(a) as c:
+        c.render(p)
+        want_a = c.readback()[0].copy()
+        c.update_scene(syn)
+        c.render(p)
+        got_syn = c.readback()[0].copy()
+        view1, _ = c.readback_view()                   # pinned view, then a bigger image, then the view again
+        assert np.array_equal(view1, want_syn)
+        c.update_scene(a)
+        c.render(p)
+        got_a = c.readback()[0].copy()
+        big = ptb.params(2 * w, 2 * h, 4, mode=1, seed=11)
+        c.render(big)
+        m_big = c.readback()[0].copy()
+        v_big, _ = c.readback_view()
+        assert np.array_equal(v_big, m_big)
+    assert np.array_equal(got_syn, want_syn)
+    assert np.array_equal(got_a, want_a)
+
+
+def test_owned_rows_only_rejects_statistics():
+    w, h = 32, 24
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        buf = c.device_alloc(w * h * 3 * 8)
+        try:
+            with pytest.raises(ptb.PtError, match="owned_rows_only"):
+                c.render_into(ptb.params(w, h, 4, mode=0, world=2, rank=0, owned_rows_only=1, collect_stats=1), buf)
+        finally:
+            c.device_free(buf)

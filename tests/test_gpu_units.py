@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import ptb, room_rays
+from conftest import ptb, orc, room_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -18,7 +18,7 @@ def test_erand48_device_matches_oracle(ctxA, golden_units):
     assert np.array_equal(got, golden_units["erand48_0_0_125"])        # the reference's own erand48
     assert got[:4].tolist() == [0.51258850097660158, 0.084069501119962808, 0.089986104133675582, 0.59578631930072845]
     import ctypes as C
-    L = ptb.load_oracle()
+    L = orc.load_oracle()
     rng = np.random.default_rng(7)
     seeds = rng.integers(0, 65536, size=(257, 3)).astype(np.uint16)
     dev = ctxA.erand48(seeds, 33)
@@ -33,7 +33,7 @@ def test_philox_device_kat_and_oracle(ctxA):
     assert out.tolist() == [[0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8], [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd],
                             [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]]
     import ctypes as C
-    L = ptb.load_oracle()
+    L = orc.load_oracle()
     rng = np.random.default_rng(8)
     ctr = rng.integers(0, 2 ** 32, size=(1000, 4), dtype=np.uint64).astype(np.uint32)
     key = rng.integers(0, 2 ** 32, size=(1000, 2), dtype=np.uint64).astype(np.uint32)
@@ -53,7 +53,7 @@ def test_ffma_peak_is_plausible(ctxA):
 def test_fp64_intersect_is_bit_exact(scene, golden_units):
     sc = ptb.builtin_scene(scene)
     rays = np.concatenate([golden_units["rays"], room_rays(100000, 11, f32_exact=False)])
-    t_o, id_o = ptb.oracle_intersect(sc, rays)
+    t_o, id_o = orc.oracle_intersect(sc, rays)
     with ptb.Context(sc) as c:
         t, ids = c.intersect(rays, 64)
     assert np.array_equal(ids, id_o)
@@ -103,7 +103,7 @@ def test_fp32_intersect_same_id_and_t_within_1e6(scene, spec):
       (iv)  |dt| <= 1e-5 * max(t, 1) on >= 99.9 % of all hits."""
     sc = ptb.builtin_scene(scene)
     rays = room_rays(400000, 12, f32_exact=True, margin=4.0)
-    t_o, id_o = ptb.oracle_intersect(sc, rays)
+    t_o, id_o = orc.oracle_intersect(sc, rays)
     with ptb.Context(sc) as c:
         c.set_specialisation(spec)      # 2: closest_hit of the NVRTC build (scene constants as immediates)
         t, ids = c.intersect(rays, 32)

@@ -4,7 +4,7 @@ pixels; in practice every pixel matches when both sides use the shared determini
 import numpy as np
 import pytest
 
-from conftest import ptb
+from conftest import ptb, orc
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-9
@@ -37,7 +37,7 @@ def test_gate1_vs_oracle_det_sincos(scene, mode):
     with ptb.Context(sc) as c:
         c.render(p)
         mean, sq, st = c.readback(True)
-    cl, omean, osq, ost = ptb.oracle_render(sc, p)
+    cl, omean, osq, ost = orc.oracle_render(sc, p)
     frac = match_fraction(mean, omean)
     assert frac >= 0.999, frac
     assert match_fraction(sq, osq) >= 0.999
@@ -54,7 +54,7 @@ def test_gate1_scene_B_with_cuda_libm():
     with ptb.Context(sc) as c:
         c.render(p)
         mean, st = c.readback()
-    omean = ptb.oracle_render(sc, p)[1]
+    omean = orc.oracle_render(sc, p)[1]
     assert match_fraction(mean, omean) >= 0.999
 
 
@@ -66,7 +66,7 @@ def test_scene_A_with_cuda_libm_diverges_by_branch_flips_only():
     with ptb.Context(sc) as c:
         c.render(p)
         mean, st = c.readback()
-    omean = ptb.oracle_render(sc, p)[1]
+    omean = orc.oracle_render(sc, p)[1]
     ok = (np.abs(mean - omean) <= RTOL * np.abs(omean)).all(axis=2)
     assert ok[:, 0].mean() > 0.9                       # rows start in sync
     for y in range(h):
@@ -85,7 +85,7 @@ def test_unpinned_features_vs_oracle_restatement(mode):
     with ptb.Context(sc) as c:
         c.render(p)
         mean, st = c.readback()
-    cl, omean, osq, ost = ptb.oracle_render(sc, p)
+    cl, omean, osq, ost = orc.oracle_render(sc, p)
     assert match_fraction(mean, omean) >= 0.995
     assert st.rays_shadow == ost.rays_shadow or match_fraction(mean, omean) < 1.0
 
@@ -94,7 +94,7 @@ def test_unpinned_features_vs_oracle_restatement(mode):
 def test_row_tile_sharding_and_ragged_tiles(h, tile, world):
     w, spp = 40, 4
     sc = ptb.builtin_scene("A", w, h)
-    full = ptb.oracle_render(sc, ptb.params(w, h, spp, mode=0, engine=1, sincos=1))[1]
+    full = orc.oracle_render(sc, ptb.params(w, h, spp, mode=0, engine=1, sincos=1))[1]
     total = np.zeros_like(full)
     with ptb.Context(sc) as c:
         for r in range(world):
@@ -115,7 +115,7 @@ def test_seed_wraps_like_the_reference_for_tall_images():
     with ptb.Context(sc) as c:
         c.render(p)
         mean, st = c.readback()
-    omean = ptb.oracle_render(sc, p)[1]
+    omean = orc.oracle_render(sc, p)[1]
     assert mean[1360:1368].any()
     assert match_fraction(mean, omean) == 1.0
 
@@ -126,7 +126,7 @@ def test_edge_cases_and_errors():
         c.render(ptb.params(1, 1, 3, mode=0, engine=1, sincos=1))
         mean, st = c.readback()
         assert mean.shape == (1, 1, 3) and st.paths == 3
-        assert match_fraction(mean, ptb.oracle_render(sc, ptb.params(1, 1, 3, mode=0, engine=1, sincos=1))[1]) == 1.0
+        assert match_fraction(mean, orc.oracle_render(sc, ptb.params(1, 1, 3, mode=0, engine=1, sincos=1))[1]) == 1.0
         c.render(ptb.params(1, 1, 0, mode=0, engine=1))          # zero samples: empty image, not an error
         mean, st = c.readback()
         assert not mean.any() and st.paths == 0
@@ -154,8 +154,8 @@ def test_gate1_full_size_c2():
     with ptb.Context(sc) as c:
         c.render(p)
         mean, st = c.readback()
-    ptb.load_oracle().oracle_set_threads(0)
-    cl, omean, osq, ost = ptb.oracle_render(sc, p)
+    orc.load_oracle().oracle_set_threads(0)
+    cl, omean, osq, ost = orc.oracle_render(sc, p)
     frac = match_fraction(mean, omean)
     assert frac >= 0.999, frac
     assert (st.paths, st.rays_shadow, st.rays_scatter, st.shaded_vertices, st.miss_events) == \

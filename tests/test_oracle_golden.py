@@ -7,7 +7,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import ptb, ROOT
+from conftest import ptb, orc, ROOT
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "smallpt_ref")
 
@@ -19,7 +19,7 @@ def test_oracle_render_bit_identical_to_reference(golden_render, scene, mode, de
     w, h, spp = (int(v) for v in golden_render["meta_whs"])
     sc = ptb.builtin_scene(scene, w, h)
     p = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP64_ERAND48, sincos=det)
-    cl, mean, sq, st = ptb.oracle_render(sc, p)
+    cl, mean, sq, st = orc.oracle_render(sc, p)
     assert np.array_equal(cl, golden_render[f"{scene}_{mode}_{det}_clamped"])
     assert np.array_equal(mean, golden_render[f"{scene}_{mode}_{det}_mean"])
     assert np.array_equal(sq, golden_render[f"{scene}_{mode}_{det}_sumsq"])
@@ -30,11 +30,11 @@ def test_oracle_is_thread_count_independent():
     # rows own their RNG stream (src/smallpt.cpp:530): OpenMP scheduling must not change the image
     sc = ptb.builtin_scene("A", 40, 30)
     p = ptb.params(40, 30, 4, mode=0, engine=1)
-    L = ptb.load_oracle()
+    L = orc.load_oracle()
     n0 = L.oracle_set_threads(0)
-    a = ptb.oracle_render(sc, p)[0]
+    a = orc.oracle_render(sc, p)[0]
     L.oracle_set_threads(1)
-    b, st = ptb.oracle_render(sc, p)[0], ptb.oracle_render(sc, p)[3]
+    b, st = orc.oracle_render(sc, p)[0], orc.oracle_render(sc, p)[3]
     L.oracle_set_threads(n0)
     assert st.threads == 1
     assert np.array_equal(a, b)
@@ -49,7 +49,7 @@ def test_ppm_writer_byte_exact(golden_render, tmp_path):
     path = str(tmp_path / "host.ppm")
     ptb.write_ppm(path, img, w, h)
     assert open(path, "rb").read() == want
-    L = ptb.load_oracle()
+    L = orc.load_oracle()
     path2 = str(tmp_path / "oracle.ppm")
     a = np.ascontiguousarray(img)
     import ctypes as C
@@ -62,10 +62,10 @@ def test_survey_appendix_f_pixels():
     sc = ptb.builtin_scene("A", 512, 512)
     # only the first row tile is rendered (tile_rows=8, world=64 -> rows 0..7), pixels of row 0 are unaffected
     p = ptb.params(512, 512, 16, mode=0, engine=1, tile_rows=8, rank=0, world=64)
-    cl = ptb.oracle_render(sc, p)[0]
+    cl = orc.oracle_render(sc, p)[0]
     assert cl[0, 0].tolist() == [0.14841266228783917, 0.21147312050371372, 0.13991414884031766]
     p = ptb.params(512, 512, 16, mode=2, engine=1, tile_rows=8, rank=0, world=64)
-    cl = ptb.oracle_render(sc, p)[0]
+    cl = orc.oracle_render(sc, p)[0]
     assert cl[0, 0].tolist() == [0.10546875, 0.31640625, 0.10546875]
 
 
@@ -79,7 +79,7 @@ def test_oracle_vs_live_reference_binary():
                                   stdout=subprocess.DEVNULL)
             want = np.fromfile(prefix + ".clamped.f64").reshape(h, w, 3)
             sc = ptb.builtin_scene(scene, w, h)
-            cl = ptb.oracle_render(sc, ptb.params(w, h, spp, mode=mode, engine=1, sincos=det))[0]
+            cl = orc.oracle_render(sc, ptb.params(w, h, spp, mode=mode, engine=1, sincos=det))[0]
             assert np.array_equal(cl, want), (scene, mode, det)
 
 
@@ -89,7 +89,7 @@ def test_fixture_statistics_scene_B():
     # image_32pps_totalrandom.ppm (scene B, uniform weight 1, 32 spp): (102.6,104.0,84.8) => no 2cos factor.
     for mode, want in ((1, (131.3, 132.8, 109.5)), (2, (102.6, 104.0, 84.8))):
         sc = ptb.builtin_scene("B", 128, 128)
-        cl = ptb.oracle_render(sc, ptb.params(128, 128, 32, mode=mode, engine=1))[0]
+        cl = orc.oracle_render(sc, ptb.params(128, 128, 32, mode=mode, engine=1))[0]
         ints = np.vectorize(ptb.to_int)(cl)
         got = ints.reshape(-1, 3).mean(axis=0)
         assert np.all(np.abs(got - np.array(want)) < 1.5), (mode, got)

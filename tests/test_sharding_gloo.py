@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ptb, ROOT
+from conftest import ptb, orc, ROOT
 
 
 def test_owned_rows_partition():
@@ -35,14 +35,15 @@ def _worker(rank, world, port, w, h, tile, out_path):
     import sys
     sys.path.insert(0, ROOT)
     from _pkg import ptb as P
+    from oracle import pyoracle as orc
     from small_pathtracer_b200 import dist as pdist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    P.load_oracle().oracle_set_threads(1)
+    orc.load_oracle().oracle_set_threads(1)
     sc = P.builtin_scene("A", w, h)
     p = P.params(w, h, 4, mode=0, engine=1, tile_rows=tile, rank=rank, world=world)
-    mean = P.oracle_render(sc, p)[1]                     # foreign rows stay zero
+    mean = orc.oracle_render(sc, p)[1]                     # foreign rows stay zero
     local = torch.from_numpy(mean * 4.0)
     full = pdist.gather_rows(local, h, tile, rank, world, dst=0)
     if rank == 0:
@@ -58,5 +59,5 @@ def test_two_rank_gather_is_bit_identical(tmp_path, h, tile):
     mp.spawn(_worker, args=(2, _free_port(), w, h, tile, out), nprocs=2, join=True)
     got = np.load(out)
     sc = ptb.builtin_scene("A", w, h)
-    want = ptb.oracle_render(sc, ptb.params(w, h, 4, mode=0, engine=1))[1] * 4.0
+    want = orc.oracle_render(sc, ptb.params(w, h, 4, mode=0, engine=1))[1] * 4.0
     assert np.array_equal(got, want)

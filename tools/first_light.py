@@ -3,6 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from _pkg import ptb
+from oracle import pyoracle as orc
 
 def main():
     w = h = 128
@@ -27,7 +28,7 @@ def main():
         d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
         d = d.astype(np.float32).astype(np.float64)
         rays = np.concatenate([o, d], 1)
-        t_o, id_o = ptb.oracle_intersect(sc, rays)
+        t_o, id_o = orc.oracle_intersect(sc, rays)
         t64, id64 = c.intersect(rays, 64)
         t32, id32 = c.intersect(rays, 32)
         print(scn, "isect fp64: id equal", np.array_equal(id_o, id64), "t bit-equal", np.array_equal(t_o, t64))
@@ -39,7 +40,7 @@ def main():
             for sincos in (0, 1):
                 p = ptb.params(w, h, 8, mode=mode, engine=1, sincos=sincos)
                 t0 = time.time(); c.render(p); mean, st = c.readback(); dt = time.time() - t0
-                cl, omean, osq, ost = ptb.oracle_render(sc, p)
+                cl, omean, osq, ost = orc.oracle_render(sc, p)
                 rel = np.abs(mean - omean) / np.maximum(np.abs(omean), 1e-300)
                 ok = (np.abs(mean - omean) <= 1e-9 * np.abs(omean)).all(axis=2)
                 print(scn, "fp64 mode", mode, "sincos", sincos, "match %.4f%% pixels, rows intact %d/%d, gpu ms %.1f" %
@@ -50,7 +51,7 @@ def main():
             p = ptb.params(w, h, 256, mode=mode, engine=0, collect_stats=1)
             c.render(p); mean, sq, st = c.readback(True)
             po = ptb.params(w, h, 256, mode=mode, engine=1)
-            cl, omean, osq, ost = ptb.oracle_render(sc, po)
+            cl, omean, osq, ost = orc.oracle_render(sc, po)
             n_s = 256
             var_g = np.maximum(sq / n_s - mean ** 2, 0) / n_s
             var_o = np.maximum(osq / n_s - omean ** 2, 0) / n_s
