@@ -4,14 +4,14 @@
   python bench.py --gpus N --steps K --warmup W            our arm (B200, CUDA kernels through the C ABI)
   python bench.py --impl reference [...]                    the reference's own CPU code on the host cores
 
-One "step" = one full render of the workload.
-  N = 1 : BASELINE.json configs[1] — built-in scene (HEAD, 17 rectangles), 512x512, 512 spp, explicit light
-          sampling (the reference's NEE) + Russian roulette, production FP32 Philox engine.
-  N > 1 : BASELINE.json configs[4] — same scene and integrator at 3840x2160, 1024 spp, interleaved 16-row tiles
-          sharded over the ranks, accumulation buffers gathered to rank 0 over NCCL (total work fixed: strong).
+One "step" = one full render of the workload.  The headline workload is the SAME at every N — BASELINE.json
+configs[4] ("C5": built-in scene A at 3840x2160, 1024 spp, the reference's explicit light sampling + Russian roulette;
+it fits one GPU at ~0.28 s per render), so the driver's 1/2/4/8-GPU values form a strong-scaling curve.  At N > 1 the
+image is sharded by interleaved 10-row tiles and assembled on rank 0.
 `value` = paths of the whole job / device time (max over ranks), inputs resident on the device.
-`e2e`   = the same metric through the C ABI with HOST buffers: scene upload (H2D), render, gather, read-back
-          of the FP64 image to host memory (D2H), wall clock, every step.
+`e2e`   = the same metric through the C ABI with HOST buffers: scene upload (H2D), render, read-back of the FP64
+          image to host memory (D2H; at N > 1 every rank DMAs its own rows into one shared host image), wall clock.
+`secondary` (N = 1): every other BASELINE config on scenes A and B, each with its own roofline.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -29,12 +29,16 @@ sys.path.insert(0, ROOT)
 METRIC = "Mpaths/s"
 WORKLOADS = {
     # name: (scene, width, height, spp, mode, description)
-    "c2": ("A", 512, 512, 512, 0, "C2: built-in scene A 512x512, 512 spp, NEE_REF_RECT + Russian roulette"),
     "c1": ("A", 512, 512, 16, 1, "C1: built-in scene A 512x512, 16 spp, cosine-weighted"),
+    "c1b": ("B", 512, 512, 16, 1, "C1/B: sphere-era scene B 512x512, 16 spp, cosine-weighted"),
+    "c2": ("A", 512, 512, 512, 0, "C2: built-in scene A 512x512, 512 spp, NEE_REF_RECT + Russian roulette"),
+    "c2b": ("B", 512, 512, 512, 3, "C2/B: sphere-era scene B 512x512, 512 spp, NEE_CONE_SPHERE + Russian roulette"),
     "c3": ("A", 512, 512, 32, 2, "C3: built-in scene A 512x512, 32 spp, uniform hemisphere"),
+    "c3b": ("B", 512, 512, 32, 2, "C3/B: sphere-era scene B 512x512, 32 spp, uniform hemisphere"),
     "c4": ("synthetic", 1920, 1080, 256, 1, "C4: synthetic 256 spheres + tilted planes 1920x1080, 256 spp, cosine"),
-    "c5": ("A", 3840, 2160, 1024, 0, "C5: built-in scene A 3840x2160, 1024 spp, NEE_REF_RECT, row-tile sharded + NCCL gather"),
+    "c5": ("A", 3840, 2160, 1024, 0, "C5: built-in scene A 3840x2160, 1024 spp, NEE_REF_RECT + Russian roulette"),
 }
+SECONDARY = ["c1", "c1b", "c2", "c2b", "c3", "c3b", "c4"]
 F_SHADE = {0: 150.0, 1: 110.0, 2: 110.0, 3: 150.0}     # algorithmic FLOPs per shaded bounce, SURVEY 8(d)
 
 
@@ -47,14 +51,17 @@ def read_peaks():
 
 
 def traffic_per_launch(workload, launches_per_step):
-    """DRAM bytes per k_bounce launch from the committed ncu --set full capture of this workload (profiles/r01_traffic.json):
-    whole-step dram__bytes_read + dram__bytes_write divided by the launches of a step, like `avg_launch_ms`."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)[workload]
-        return t["dram_bytes_per_step"] / max(1, launches_per_step)
-    except Exception:                   # noqa: BLE001
-        return None
+    """DRAM bytes per k_bounce launch — a PROFILE CONSTANT, not measured in this run: whole-step dram__bytes_read +
+    dram__bytes_write of the committed ncu --set full capture of this workload (profiles/r02_traffic.json, falling back
+    to round 1's file) divided by the launches of a step, like `avg_launch_ms`.  None when no capture exists."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)[workload]
+            return t["dram_bytes_per_step"] / max(1, launches_per_step), f"profiles/{name} (ncu --set full capture, constant)"
+        except Exception:               # noqa: BLE001
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -162,13 +169,16 @@ def cpu_reference(workload, budget_s, threads=0):
 
 
 def secondary(ptb, workload, peak_tf, device_index, stream, flush):
-    """One warm-up + two timed renders of another configuration, device-timed by the library's CUDA events."""
+    """One warm-up + two timed renders of another configuration, device-timed by the library's CUDA events.
+    The scene-specialised kernel is forced (pt_set_specialisation 2): a render this small would otherwise start on the
+    generic kernel and get its specialised build in the background."""
     scene_name, w, h, spp, mode, desc = WORKLOADS[workload]
     scene = ptb.builtin_scene(scene_name, w, h)
     with ptb.Context(scene, device=device_index) as c:
+        c.set_specialisation(2)
         p = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0)
         best = None
-        for i in range(3):
+        for i in range(4):
             flush.fill_(1)
             stream.synchronize()
             c.render(p)
@@ -179,7 +189,8 @@ def secondary(ptb, workload, peak_tf, device_index, stream, flush):
         tf = flops / (best.render_ms * 1e-3) / 1e12
         return {"workload": desc, "value": best.paths / best.render_ms * 1e-3, "unit": METRIC, "mrays_per_s": best.rays / best.render_ms * 1e-3,
                 "ms_per_step": best.render_ms, "rays_per_path": best.rays / best.paths, "launches_per_step": int(best.iterations),
-                "specialised": bool(best.specialised),
+                "phases_ms": {"generating": best.main_kernel_ms, "tail": best.tail_ms, "resolve": best.resolve_ms, "tail_launches": int(best.tail_launches)},
+                "max_depth": int(best.max_depth_seen), "specialised": bool(best.specialised),
                 "roofline": {"bound": "fp32", "kernel": "k_bounce", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                              "flops_per_ray": scene.flops_per_ray(), "flops_per_bounce": F_SHADE[mode]}}
 
@@ -190,18 +201,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--assembly", default="auto", choices=["auto", "nccl"], help="N > 1: auto = peer-memory stores when CUDA IPC works, else NCCL gather")
     ap.add_argument("--no-ffma-peak", action="store_true", help="roofline against the theoretical FP32 peak (keeps the microbenchmark out of an ncu launch list)")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the extra C4 (intersection-bound) measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (N = 1) / the NCCL-gather and single-GPU legs (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
-    workload = args.workload or ("c2" if n_gpus == 1 else "c5")
+    workload = args.workload
     scene_name, w, h, spp, mode, desc = WORKLOADS[workload]
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -222,7 +233,7 @@ def main():
         info["value"] = value
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / max(1, args.steps), "higher_is_better": True,
-                "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "note": "CPU: each step is a bounded sample (reduced spp) of the workload"},
                 "cpu_baseline": info,
                 "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -269,41 +280,51 @@ def main():
         except RuntimeError:
             shared, assembly = None, "pack + NCCL gather to rank 0 + de-interleave"
 
-    def step(timed):
-        """one render of this rank's tiles + assembly on rank 0; returns (device ms, stats)"""
+    def step(use_shared=True):
+        """one render of this rank's tiles + assembly on rank 0; returns (device ms, stats, image, ms until this rank's own
+        render had finished)"""
         flush.fill_(1)                                                    # L2 flush between iterations
         stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if shared is not None:
+        e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if shared is not None and use_shared:
             e0.record(stream)
-            full = shared.render(params, stream.cuda_stream)
+            full = shared.render(params, stream.cuda_stream, barrier=False)
+            em.record(stream)
+            if world > 1:
+                dist.barrier()
             st = ctx.stats()
         else:
             local = torch.empty((h, w, 3), dtype=torch.float64, device=device)
             e0.record(stream)
             ctx.render_into(params, local.data_ptr(), stream.cuda_stream)
+            em.record(stream)
             st = ctx.stats()
             full = pdist.gather_rows(local, h, tile_rows, rank, world, dst=0) if world > 1 else local
         e1.record(stream)
         e1.synchronize()
-        ms = e0.elapsed_time(e1)              # render (all k_bounce launches + resolve) + gather, on `stream`
-        return ms, st, full
+        return e0.elapsed_time(e1), st, full, e0.elapsed_time(em)     # render (all k_bounce launches + resolve) + assembly, on `stream`
 
     for _ in range(warmup):
-        step(False)
+        step()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.05)
     barrier()
     t_wall0 = time.perf_counter()
     ms_steps, stats, launches, kernel_ms, iters = [], None, 0, 0.0, 0
+    ph = {"generating": 0.0, "tail": 0.0, "resolve": 0.0, "own_render": 0.0, "wait_and_barrier": 0.0}
     for _ in range(args.steps):
-        ms, st, full = step(True)
+        ms, st, full, ms_own = step()
         ms_steps.append(ms)
         stats = st
         launches += st.kernel_launches
         kernel_ms += st.render_ms
         iters += st.iterations
+        ph["generating"] += st.main_kernel_ms
+        ph["tail"] += st.tail_ms
+        ph["resolve"] += st.resolve_ms
+        ph["own_render"] += ms_own
+        ph["wait_and_barrier"] += ms - ms_own
     barrier()
     t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -312,26 +333,47 @@ def main():
     my_rays = float(stats.rays) * args.steps
     my_shaded = float(stats.shaded_vertices) * args.steps
     agg = torch.tensor([total_ms, my_paths, my_rays, my_shaded, float(launches), kernel_ms], dtype=torch.float64, device=device)
+    ph_keys = sorted(ph)
+    ph_t = torch.tensor([ph[k] / args.steps for k in ph_keys], dtype=torch.float64, device=device)
+    ph_min = ph_t.clone()
     if world > 1:
         tmax = agg[:1].clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         sums = agg[1:].clone()
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ph_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
         total_ms = float(tmax[0])
         paths, rays, shaded, launches_all, kernel_ms_all = (float(x) for x in sums)
     else:
         paths, rays, shaded, launches_all, kernel_ms_all = my_paths, my_rays, my_shaded, float(launches), kernel_ms
+    phases = {k: {"max_over_ranks_ms": float(ph_t[i]), "min_over_ranks_ms": float(ph_min[i])} for i, k in enumerate(ph_keys)}
+    phases["note"] = ("per step; generating / tail / resolve from %globaltimer stamps the kernels take themselves (pt_stats), own_render = CUDA events "
+                      "around this rank's pt_render_into, wait_and_barrier = the rest of the step (waiting for the slowest rank + the barrier / gather)")
     value = paths / total_ms * 1e-3
     mrays = rays / total_ms * 1e-3
 
     # ------------------------------------------------------------------ e2e: host buffers through the C ABI
-    host_img = np.empty((h, w, 3), dtype=np.float64)                       # the caller's result buffer, re-used every step
-    host_pinned = torch.empty((h, w, 3), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
+    # N = 1: pt_scene_upload + pt_render + pt_readback_view (one DMA into the context's pinned image).
+    # N > 1: every rank renders its tiles and DMAs ITS rows into ONE host image in shared memory (pt_readback_owned),
+    #        each over its own PCIe link; rank 0's host then holds the whole FP64 picture.
+    host_img = None
+    if world > 1:
+        try:
+            host_img = pdist.HostImage(ctx, h, w, rank, world, dst=0)
+        except Exception:               # noqa: BLE001
+            host_img = None
+    host_pinned = torch.empty((h, w, 3), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0 and host_img is None) else None
 
     def e2e_step():
         t0 = time.perf_counter()
         ctx.update_scene(scene)                                             # H2D: scene table + camera (pt_scene_upload, in place)
-        if world > 1:
+        if world > 1 and host_img is not None:
+            ctx.render(params)                                              # this rank's tiles into its own accumulators
+            ctx.readback_owned(host_img.array)                              # D2H: its rows into the shared host image
+            dist.barrier()
+            host = host_img.array if rank == 0 else None
+        elif world > 1:
             if shared is not None:
                 full = shared.render(params, stream.cuda_stream)
             else:
@@ -341,13 +383,15 @@ def main():
                 host_pinned.copy_(full / float(spp), non_blocking=True)
                 torch.cuda.current_stream(device).synchronize()
                 host = host_pinned.numpy()
+            dist.barrier()
         else:
             ctx.render(params)
             host, _ = ctx.readback_view()                                   # D2H inside pt_readback_view (context-owned pinned image)
-        if world > 1:
-            dist.barrier()
         return time.perf_counter() - t0, host
-    e2e_step()
+    _, img_e2e = e2e_step()
+    e2e_check = None
+    if rank == 0 and world > 1 and full is not None:                        # the host-assembled picture is the device-assembled one
+        e2e_check = bool(np.array_equal(np.asarray(img_e2e), (full / float(spp)).cpu().numpy()))
     barrier()
     e2e_times = []
     for _ in range(max(1, min(args.steps, 10))):
@@ -357,9 +401,21 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = (paths / args.steps) * len(e2e_times) / float(e2e_t[0]) * 1e-6
-    # strong-scaling reference measured in the same job: rank 0 renders the WHOLE workload alone (the other ranks wait)
-    single_ms = None
-    if world > 1:
+
+    # N > 1, same job: (a) the NCCL-gather assembly, (b) the whole workload on rank 0 alone (strong-scaling reference)
+    nccl_leg, single_ms = None, None
+    if world > 1 and not args.no_secondary:
+        if shared is not None:
+            t_n = []
+            for i in range(3):
+                barrier()
+                ms, _st, _f, _o = step(use_shared=False)
+                if i > 0:
+                    t_n.append(ms)
+            t_nccl = torch.tensor([sum(t_n) / len(t_n)], dtype=torch.float64, device=device)
+            dist.all_reduce(t_nccl, op=dist.ReduceOp.MAX)
+            nccl_leg = {"assembly": "pack + NCCL gather to rank 0 + de-interleave", "ms_per_step": float(t_nccl[0]),
+                        "value": (paths / args.steps) / float(t_nccl[0]) * 1e-3, "unit": METRIC}
         if rank == 0:
             p1 = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=0, world=1)
             for _ in range(2):
@@ -388,22 +444,25 @@ def main():
     fp32_theory = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
     f_isect = scene.flops_per_ray()
     my_flops = float(stats.rays) * f_isect + float(stats.shaded_vertices) * F_SHADE[mode]     # per step, this rank
-    k_ms = stats.render_ms                                                                   # CUDA events around the launches
+    k_ms = stats.main_kernel_ms + stats.tail_ms                                              # the k_bounce launches of a step (%globaltimer stamps)
+    if not k_ms > 0:
+        k_ms = stats.render_ms
     achieved_tf = my_flops / (k_ms * 1e-3) / 1e12
     per_launch_ms = k_ms / max(1, stats.iterations)
     qbytes = 48.0 * float(stats.queue_slots_io)                       # 48 B per path record read or written through the queues
+    traffic, traffic_src = traffic_per_launch(workload, int(stats.iterations))
     roofline = {"bound": "fp32", "kernel": "k_bounce", "achieved": achieved_tf, "peak": ffma_tf or fp32_theory, "unit": "TFLOP/s",
                 "frac": achieved_tf / (ffma_tf or fp32_theory),
                 "peak_source": "FFMA-only microbenchmark measured in this run (pt_debug_ffma_peak)" if ffma_tf else f"{n_sm} SM x 128 lanes x 2 x sm_max_mhz",
                 "peak_theoretical": fp32_theory, "frac_of_theoretical": achieved_tf / fp32_theory,
                 "flops_per_ray": f_isect, "flops_per_bounce": F_SHADE[mode],
                 "avg_launch_ms": per_launch_ms, "launches_per_step": int(stats.iterations),
-                "traffic": traffic_per_launch(workload, int(stats.iterations)),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "queue": {"bound": "hbm", "achieved": qbytes / (k_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                           "frac": qbytes / (k_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src,
                           "note": "path records through the wavefront queues x 48 B (a slot advances several bounces per launch in registers)"}}
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "engine": "FP32 Philox wavefront", "tile_rows": tile_rows, "parallelism": f"row-tiles x{world}", "assembly": assembly,
                        "l2": "256 MiB flush write between timed iterations", "paths_per_step": paths / args.steps,
@@ -412,20 +471,32 @@ def main():
                                   if stats.specialised else "generic k_bounce (scene in __constant__ memory)"),
                        "bounces_per_launch": 512},
             "mrays_per_s": mrays, "wall_ms_per_step": (t_wall1 - t_wall0) * 1e3 / args.steps,
-            "clocks": clocks, "gpu_launches": int(launches_all),
+            "clocks": clocks, "gpu_launches": int(launches_all), "phases": phases,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback_view (FP64 mean image device->pinned host) per step, wall clock"},
+                    "note": ("pt_scene_upload (scene tables host->device, context re-used) + pt_render + pt_readback_view (FP64 mean image device->pinned host) per step, wall clock"
+                             if world == 1 else
+                             ("pt_scene_upload + pt_render of this rank's tiles + pt_readback_owned: every rank DMAs its rows into ONE shared, page-locked host image "
+                              "over its own PCIe link + one barrier, wall clock, max over ranks" if host_img is not None else
+                              "pt_scene_upload + sharded render + assembled image read back through rank 0, wall clock"))},
             "roofline": roofline}
+    if e2e_check is not None:
+        line["e2e"]["host_image_equals_device_image"] = e2e_check
     if single_ms:
         line["strong_scaling"] = {"single_gpu_ms_per_step": single_ms, "n_gpu_ms_per_step": total_ms / args.steps,
                                   "speedup": single_ms / (total_ms / args.steps), "n_gpus": n_gpus,
                                   "note": "same workload rendered by rank 0 alone in this job (render only, no gather) vs the sharded step incl. gather"}
-    if n_gpus == 1 and not args.no_secondary and workload == "c2":
-        # the intersection-bound configuration (C4) next to the headline: same engine, same accounting
-        try:
-            line["secondary"] = {"c4": secondary(ptb, "c4", ffma_tf or fp32_theory, local_rank, stream, flush)}
-        except Exception as e:                                           # noqa: BLE001
-            line["secondary"] = {"error": str(e)}
+    if nccl_leg:
+        line["nccl_assembly"] = nccl_leg
+    if n_gpus == 1 and not args.no_secondary:
+        # every other BASELINE config, scenes A and B: same engine, same accounting, each with its own roofline
+        line["secondary"] = {}
+        for name in SECONDARY:
+            if name == workload:
+                continue
+            try:
+                line["secondary"][name] = secondary(ptb, name, ffma_tf or fp32_theory, local_rank, stream, flush)
+            except Exception as e:                                       # noqa: BLE001
+                line["secondary"][name] = {"error": str(e)}
     if n_gpus == 1 and not args.no_cpu_baseline:
         try:
             info, _ = cpu_reference(workload, args.cpu_budget)

@@ -154,8 +154,21 @@ typedef struct pt_stats {
     uint32_t max_depth_seen;
     uint32_t specialised;       /* 1 = the last FP32 render ran the scene-specialised (NVRTC) build of k_bounce */
     double   render_ms;         /* device time of the last pt_render (CUDA events)       */
-    double   main_kernel_ms;    /* summed device time of the dominant kernel             */
+    double   main_kernel_ms;    /* FP32 engine: device time of the k_bounce launches that still generated camera paths */
     uint64_t queue_slots_io;    /* path records read + written through the wavefront queues */
+    /* phases of the last FP32 render, from %globaltimer stamps taken by the kernels themselves (they add up to
+     * render_ms minus the memsets / constant uploads in front of the first launch) */
+    double   tail_ms;           /* k_bounce launches after generation was exhausted (the survivors of long paths) */
+    double   resolve_ms;        /* fixed point -> FP64 sums, incl. the peer-memory stores of owned_rows_only */
+    uint64_t tail_launches;     /* how many of `iterations` belong to tail_ms */
+    /* collect_stats = 1 only (the reference's sole counters are path_length and the progress print,
+     * src/smallpt.cpp:529,543): why paths ended, and how many were alive at each depth */
+    uint64_t term_roulette;     /* ended by Russian roulette on a surface with albedo > 0 (:449, depth > 5)            */
+    uint64_t term_emitter;      /* ended on a surface with albedo 0 (the `!p` arm of :448: light sources)              */
+    uint64_t term_light_sample; /* NEE_REF_RECT: finished in place along a visible light sample (:466-473)             */
+    uint64_t dropped_contributions; /* radiance contributions that were NaN, negative or clamped (>= 6e10): not added  */
+    uint64_t spawned_branches;  /* second REFR branches spawned while depth <= 2 (:494-495)                             */
+    uint64_t live_at_depth[64]; /* [d] = paths that shaded a vertex at depth d+1 (last bucket: depth >= 64)             */
 } pt_stats;
 
 typedef enum pt_status {
@@ -215,6 +228,15 @@ int pt_ipc_close(pt_ctx *ctx, void *dev_ptr);
  * from the device, no host-side copy).  The pointer stays valid until the next pt_readback_view / pt_destroy on this
  * context; NULL on error (pt_last_error).  A host loop such as src/smallpt.cpp:538 can read it in place. */
 const double *pt_readback_view(pt_ctx *ctx, pt_stats *stats);
+
+/* Multi-process host-side assembly: the rows THIS rank owns (row tiles k % world == rank of the last pt_render), as
+ * means, into the caller's full-size host image (w*h*3 doubles) — one DMA per row tile, every rank over its own PCIe
+ * link.  When all ranks map the same image (POSIX shared memory) the picture of src/smallpt.cpp:538 assembles in
+ * host memory without funnelling through one GPU.  pt_host_register page-locks caller-owned memory for those DMAs
+ * (cudaHostRegister); unregistered memory works too, through the driver's staging. */
+int pt_host_register(pt_ctx *ctx, void *host_ptr, size_t bytes);
+int pt_host_unregister(pt_ctx *ctx, void *host_ptr);
+int pt_readback_owned(pt_ctx *ctx, double *host_image, pt_stats *stats);
 
 /* Resume from a checkpoint: load per-pixel SUMS (and optionally sums of squares) of `spp_done` samples — what
  * pt_accum_download returned earlier, possibly in another process — into the context's accumulators, so that a

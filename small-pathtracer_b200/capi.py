@@ -67,10 +67,13 @@ class Stats(C.Structure):
                 ("rays_shadow", C.c_uint64), ("shaded_vertices", C.c_uint64), ("miss_events", C.c_uint64),
                 ("truncated", C.c_uint64), ("kernel_launches", C.c_uint64), ("iterations", C.c_uint64),
                 ("max_depth_seen", C.c_uint32), ("specialised", C.c_uint32),
-                ("render_ms", C.c_double), ("main_kernel_ms", C.c_double), ("queue_slots_io", C.c_uint64)]
+                ("render_ms", C.c_double), ("main_kernel_ms", C.c_double), ("queue_slots_io", C.c_uint64),
+                ("tail_ms", C.c_double), ("resolve_ms", C.c_double), ("tail_launches", C.c_uint64),
+                ("term_roulette", C.c_uint64), ("term_emitter", C.c_uint64), ("term_light_sample", C.c_uint64),
+                ("dropped_contributions", C.c_uint64), ("spawned_branches", C.c_uint64), ("live_at_depth", C.c_uint64 * 64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
+        return {n: (list(getattr(self, n)) if n == "live_at_depth" else getattr(self, n)) for n, _ in self._fields_ if not n.startswith("_")}
 
     @property
     def rays(self):
@@ -269,7 +272,7 @@ def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, s
 # ------------------------------------------------------------------------------ product library
 _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
-EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_accum_device_ptr",
+EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_readback_owned", "pt_host_register", "pt_host_unregister", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_ffma_peak",
            "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
@@ -292,6 +295,9 @@ def lib():
         L.pt_ipc_export.argtypes = [vp, vp, C.c_char_p]
         L.pt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.pt_ipc_close.argtypes = [vp, vp]
+        L.pt_readback_owned.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(Stats)]
+        L.pt_host_register.argtypes = [vp, vp, C.c_size_t]
+        L.pt_host_unregister.argtypes = [vp, vp]
         L.pt_readback_view.argtypes = [vp, C.POINTER(Stats)]
         L.pt_readback_view.restype = C.POINTER(C.c_double)
         L.pt_accum_upload.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
@@ -401,6 +407,19 @@ class Context:
         if not ptr:
             self._check(-3, "pt_readback_view")
         return np.ctypeslib.as_array(ptr, shape=(p.height, p.width, 3)), st
+
+    def readback_owned(self, host_image):
+        """This rank's rows (means) into a full-size (H, W, 3) float64 host image shared by the ranks (dist.HostImage)."""
+        st = Stats()
+        assert host_image.dtype == np.float64 and host_image.flags.c_contiguous
+        self._check(lib().pt_readback_owned(self._h, _dp(host_image), C.byref(st)), "pt_readback_owned")
+        return st
+
+    def host_register(self, arr):
+        self._check(lib().pt_host_register(self._h, C.c_void_p(arr.ctypes.data), arr.nbytes), "pt_host_register")
+
+    def host_unregister(self, arr):
+        self._check(lib().pt_host_unregister(self._h, C.c_void_p(arr.ctypes.data)), "pt_host_unregister")
 
     # ---- peer-memory plumbing (fused resolve + gather, dist.SharedImage)
     def device_alloc(self, nbytes):

@@ -356,6 +356,9 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     st.render_ms = ms;
     st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
     st.shaded_vertices = ds.shaded; st.max_depth_seen = ds.max_depth_seen;
+    st.term_roulette = ds.term_roulette; st.term_emitter = ds.term_emitter; st.term_light_sample = ds.term_light_sample;
+    st.dropped_contributions = ds.dropped; st.spawned_branches = ds.spawned;
+    for (int k = 0; k < 64; k++) st.live_at_depth[k] = ds.live_at_depth[k];
     st.specialised = ctx->jit ? 1u : 0u;
     if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode == 1 && !ctx->jit)
         pt_jit_account(ctx, p->mode, p->collect_stats != 0, ms);      // small render, generic kernel: counts towards its background build
@@ -737,6 +740,56 @@ const double *pt_readback_view(pt_ctx *ctx, pt_stats *stats)
     return ctx->h_view;
 }
 
+int pt_host_register(pt_ctx *ctx, void *host_ptr, size_t bytes)
+{
+    if (!ctx || !host_ptr || bytes == 0) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return PT_OK;
+}
+
+int pt_host_unregister(pt_ctx *ctx, void *host_ptr)
+{
+    if (!ctx || !host_ptr) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    PT_CUDA(ctx, cudaHostUnregister(host_ptr));
+    return PT_OK;
+}
+
+// The rows this rank owns (row tiles k % world == rank of the last render), as means, into the caller's FULL-SIZE
+// host image: one DMA per row tile, each rank over its own PCIe link.  With the image in memory every rank maps
+// (POSIX shared memory, registered through pt_host_register) the host-side image assembles without a gather.
+int pt_readback_owned(pt_ctx *ctx, double *host_image, pt_stats *stats)
+{
+    if (!ctx || !host_image) return pt_fail(ctx, PT_ERR_ARG, "bad argument");
+    if (!ctx->rendered) return pt_fail(ctx, PT_ERR_STATE, "pt_readback_owned before a successful pt_render");
+    PT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const pt_render_params &p = ctx->last;
+    if (ctx->d_sum_ext && p.owned_rows_only)
+        return pt_fail(ctx, PT_ERR_STATE, "the last render stored its rows into a shared image (owned_rows_only): read that image instead");
+    const size_t n = (size_t)p.width * p.height * 3;
+    if (ctx->mean_elems < n) {
+        if (ctx->d_mean) cudaFree(ctx->d_mean);
+        ctx->d_mean = nullptr; ctx->mean_elems = 0;
+        PT_CUDA(ctx, cudaMalloc(&ctx->d_mean, n * sizeof(double)));
+        ctx->mean_elems = n;
+    }
+    const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
+    const double spp = (double)(ctx->accum_spp > 0 ? ctx->accum_spp : p.spp);
+    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, spp > 0 ? 1.0 / spp : 1.0);
+    PT_CUDA(ctx, cudaGetLastError());
+    const int world = p.world > 0 ? p.world : 1, tile = p.tile_rows > 0 ? p.tile_rows : 8;
+    const int n_tiles = (p.height + tile - 1) / tile;
+    const size_t row = (size_t)p.width * 3;
+    for (int k = p.rank; k < n_tiles; k += world) {
+        const int y0 = k * tile, rows = std::min(tile, p.height - y0);
+        PT_CUDA(ctx, cudaMemcpyAsync(host_image + (size_t)y0 * row, ctx->d_mean + (size_t)y0 * row, (size_t)rows * row * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) *stats = ctx->stats;
+    return PT_OK;
+}
+
 void *pt_accum_device_ptr(pt_ctx *ctx) { return ctx ? (void *)(ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum) : nullptr; }
 
 int pt_debug_intersect(pt_ctx *ctx, const double *rays_od, int n, int precision, double *t_out, int *id_out)
@@ -821,7 +874,10 @@ void pt_destroy(pt_ctx *ctx)
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 4; b++) if (ctx->q[a][b]) cudaFree(ctx->q[a][b]);
     if (ctx->d_warp_chunk) cudaFree(ctx->d_warp_chunk);
+    if (ctx->d_spawn) cudaFree(ctx->d_spawn);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
+    if (ctx->d_launch_rec) cudaFree(ctx->d_launch_rec);
+    if (ctx->d_stamps) cudaFree(ctx->d_stamps);
     if (ctx->d_fix) cudaFree(ctx->d_fix);
     if (ctx->d_fixsq) cudaFree(ctx->d_fixsq);
     if (ctx->d_sum) cudaFree(ctx->d_sum);

@@ -69,9 +69,13 @@ struct pt_ctx {
     float4 *q[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     int q_capacity = 0;
     uint4 *d_warp_chunk = nullptr;                     // per warp: path indices reserved but not yet traced
+    float4 *d_spawn = nullptr;                         // per-warp stacks of spawned REFR branches (scenes with REFR only)
+    int spawn_warps = 0;
     unsigned int *d_counts = nullptr;                  // per-iteration live counts etc.
     int counts_len = 0;
     size_t counts_dirty = 0;
+    LaunchRec *d_launch_rec = nullptr;                 // one record per k_bounce launch (phase split of pt_stats)
+    unsigned long long *d_stamps = nullptr;            // %globaltimer at the start of the resolve kernel and at the end of the render
     unsigned int *h_pinned = nullptr;                  // 2 pinned words for the termination check
     cudaEvent_t ev_batch[2] = {nullptr, nullptr};
     DevStats *h_stats = nullptr;                       // pinned

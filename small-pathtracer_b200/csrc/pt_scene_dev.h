@@ -69,6 +69,17 @@ struct MatF32 {                   // global memory, indexed by CODE (divergent i
 struct DevStats {                 // device-side counters (unsigned long long for atomicAdd)
     unsigned long long paths, rays_camera, rays_scatter, rays_shadow, shaded, misses, truncated;
     unsigned int max_depth_seen, pad;
+    // collect_stats only
+    unsigned long long term_roulette, term_emitter, term_light_sample, dropped, spawned;
+    unsigned long long live_at_depth[64];
 };
+
+// One record per k_bounce launch, written by the launch itself (block 0, thread 0): when it started and in which phase.
+struct LaunchRec {
+    unsigned long long t_start;   // %globaltimer, ns
+    unsigned int exhausted;       // 1 = every camera path had been handed out when this launch started (tail)
+    unsigned int n_in;            // live path slots it found in its input queue
+};
+#define PT_MAX_LAUNCH_RECS 4096
 
 #endif

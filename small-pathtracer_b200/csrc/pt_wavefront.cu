@@ -30,6 +30,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "pt_internal.h"
@@ -39,9 +40,10 @@ namespace {
 
 // fixed point -> double sums, restricted to the rows this rank owns (foreign rows stay zero)
 __global__ void k_resolve(const unsigned long long *__restrict__ fix, const unsigned long long *__restrict__ fixsq,
-                          double *__restrict__ sum, double *__restrict__ sumsq, size_t n)
+                          double *__restrict__ sum, double *__restrict__ sumsq, size_t n, unsigned long long *stamp)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *stamp = global_timer_ns();
     if (i >= n) return;
     sum[i] = (double)fix[i] * PT_FIX_INV;
     if (sumsq && fixsq) sumsq[i] = (double)fixsq[i] * PT_FIX_INV;
@@ -50,9 +52,10 @@ __global__ void k_resolve(const unsigned long long *__restrict__ fix, const unsi
 // the same for the rows of this rank only (owned_rows_only): `sum` may be another GPU's image, written over NVLink
 // peer memory — the gather of the row tiles is these stores
 __global__ void k_resolve_owned(const unsigned long long *__restrict__ fix, double *__restrict__ sum, unsigned long long owned_pixels,
-                                int w, int tile_rows, int rank, int world)
+                                int w, int tile_rows, int rank, int world, unsigned long long *stamp)
 {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *stamp = global_timer_ns();
     if (i >= owned_pixels * 3ull) return;
     const unsigned long long lp = i / 3ull;
     const unsigned int ch = (unsigned int)(i - lp * 3ull);
@@ -62,6 +65,9 @@ __global__ void k_resolve_owned(const unsigned long long *__restrict__ fix, doub
     const size_t idx = ((size_t)y * (size_t)w + x) * 3 + ch;
     sum[idx] = (double)fix[idx] * PT_FIX_INV;
 }
+
+// end-of-render time stamp (one thread)
+__global__ void k_stamp(unsigned long long *stamp) { *stamp = global_timer_ns(); }
 
 __global__ void k_philox(const uint32_t *__restrict__ ctr, const uint32_t *__restrict__ key, int n, uint32_t *__restrict__ out)
 {
@@ -91,15 +97,16 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
-template <int MODE> void launch_bounce(bool stats, int blocks, cudaStream_t s, const KParams &P, const PtJitKernel *jk)
+template <int MODE> void launch_bounce(bool stats, bool glossy, int blocks, cudaStream_t s, const KParams &P, const PtJitKernel *jk)
 {
     if (jk) {           // scene-specialised module (pt_jit.cu): same KParams, launched through its kernel handle
         void *args[] = {(void *)&P};
         cudaLaunchKernel((const void *)jk->kern, dim3(blocks), dim3(PT_BLOCK), args, 0, s);
         return;
     }
-    if (stats) k_bounce<MODE, true><<<blocks, PT_BLOCK, 0, s>>>(P);
-    else k_bounce<MODE, false><<<blocks, PT_BLOCK, 0, s>>>(P);
+    // ahead-of-time build: DIFF-only scenes (every scene of the reference) run the instantiation without SPEC / REFR code
+    if (stats) { if (glossy) k_bounce<MODE, true, true><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, true, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
+    else { if (glossy) k_bounce<MODE, false, true><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, false, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
 }
 
 }  // namespace
@@ -191,6 +198,15 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             if (dirty > (size_t)ctx->counts_len) dirty = (size_t)ctx->counts_len;
             PT_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned int) * dirty, s));
         }
+        // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
+        const bool want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
+        if (want_spawn && ctx->spawn_warps < cap / 32) {
+            if (ctx->d_spawn) cudaFree(ctx->d_spawn);
+            ctx->d_spawn = nullptr; ctx->spawn_warps = 0;
+            PT_CUDA(ctx, cudaMalloc(&ctx->d_spawn, sizeof(float4) * (3 * PT_SPAWN_SLOTS + 32) * (size_t)(cap / 32)));
+            ctx->spawn_warps = cap / 32;
+        }
+        if (!ctx->d_launch_rec) PT_CUDA(ctx, cudaMalloc(&ctx->d_launch_rec, sizeof(LaunchRec) * (PT_MAX_LAUNCH_RECS + 1)));
         PT_CUDA(ctx, cudaMemsetAsync(ctx->d_warp_chunk, 0, sizeof(uint4) * (size_t)(cap / 32), s));   // n[0] = 0: every slot starts without a path
         const PtJitKernel *jk = ctx->jit;
         if (jk) {       // the specialised module has its own c_scene (lights, huge spheres, tilted planes, overflow)
@@ -249,8 +265,11 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         philox_round_keys(P.seed_lo, P.seed_hi, P.philox_rk);
         P.fix = ctx->d_fix; P.fixsq = ctx->d_fixsq;
         P.mats = ctx->d_mats; P.sphf = ctx->d_sphf; P.stats = ctx->d_stats;
+        P.spawn = want_spawn ? ctx->d_spawn : nullptr;
+        P.spawn_slots = want_spawn ? PT_SPAWN_SLOTS : 0u;
 
         const int blocks = cap / PT_BLOCK;
+        const bool glossy = (ctx->h_scene32->refl_mask & ((1 << PT_SPEC) | (1 << PT_REFR))) != 0;
         unsigned int *n_it = ctx->d_counts + 2;
         // Termination check without draining the pipeline: batch k+1 is enqueued before the live count
         // after batch k is read back (pinned slot + event per parity).
@@ -265,11 +284,12 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
                 for (int a = 0; a < 4; a++) { P.qin[a] = ctx->q[it & 1][a]; P.qout[a] = ctx->q[(it + 1) & 1][a]; }
                 P.n_in = n_it + it; P.n_out = n_it + it + 1;
                 P.first_launch = it == 0 ? 1 : 0;
+                P.launch_rec = ctx->d_launch_rec + std::min(it, PT_MAX_LAUNCH_RECS - 1);
                 switch (p->mode) {
-                case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, blocks, s, P, jk); break;
-                case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, blocks, s, P, jk); break;
-                case PT_MODE_UNI: launch_bounce<PT_MODE_UNI>(stats, blocks, s, P, jk); break;
-                default: launch_bounce<PT_MODE_NEE_CONE_SPHERE>(stats, blocks, s, P, jk); break;
+                case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, glossy, blocks, s, P, jk); break;
+                case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, glossy, blocks, s, P, jk); break;
+                case PT_MODE_UNI: launch_bounce<PT_MODE_UNI>(stats, glossy, blocks, s, P, jk); break;
+                default: launch_bounce<PT_MODE_NEE_CONE_SPHERE>(stats, glossy, blocks, s, P, jk); break;
                 }
                 ctx->stats.kernel_launches++;
             }
@@ -289,22 +309,49 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         ctx->counts_dirty = (size_t)it + 4;
         it_total = it;
     }
-    if (p->owned_rows_only && !stats) {
+    if (!ctx->d_stamps) PT_CUDA(ctx, cudaMalloc(&ctx->d_stamps, 2 * sizeof(unsigned long long)));
+    if (p->owned_rows_only) {          // (render_common rejects owned_rows_only together with collect_stats)
         if (owned_pixels > 0)
-            k_resolve_owned<<<(unsigned)((owned_pixels * 3ull + 255) / 256), 256, 0, s>>>(ctx->d_fix, d_sum, owned_pixels, w, tile, p->rank, world);
+            k_resolve_owned<<<(unsigned)((owned_pixels * 3ull + 255) / 256), 256, 0, s>>>(ctx->d_fix, d_sum, owned_pixels, w, tile, p->rank, world, ctx->d_stamps);
+        else k_stamp<<<1, 1, 0, s>>>(ctx->d_stamps);
     } else {
-        k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc);
+        k_resolve<<<(unsigned)((n_acc + 255) / 256), 256, 0, s>>>(ctx->d_fix, stats ? ctx->d_fixsq : nullptr, d_sum, stats ? d_sumsq : nullptr, n_acc, ctx->d_stamps);
     }
-    ctx->stats.kernel_launches++;
+    k_stamp<<<1, 1, 0, s>>>(ctx->d_stamps + 1);
+    ctx->stats.kernel_launches += 2;
     PT_CUDA(ctx, cudaGetLastError());
     ctx->stats.queue_slots_io = 0;
+    ctx->stats.main_kernel_ms = ctx->stats.tail_ms = ctx->stats.resolve_ms = 0.0;
+    ctx->stats.tail_launches = 0;
     if (it_total > 0) {   // queue traffic of this render: launch k reads n[k] slots and writes n[k+1]
         std::vector<unsigned int> h(it_total + 1);
+        const int n_rec = std::min(it_total, PT_MAX_LAUNCH_RECS);
+        std::vector<LaunchRec> rec(n_rec);
+        unsigned long long stamps[2] = {0, 0};
         PT_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts + 2, sizeof(unsigned int) * (size_t)(it_total + 1), cudaMemcpyDeviceToHost, s));
+        PT_CUDA(ctx, cudaMemcpyAsync(rec.data(), ctx->d_launch_rec, sizeof(LaunchRec) * (size_t)n_rec, cudaMemcpyDeviceToHost, s));
+        PT_CUDA(ctx, cudaMemcpyAsync(stamps, ctx->d_stamps, sizeof stamps, cudaMemcpyDeviceToHost, s));
         PT_CUDA(ctx, cudaStreamSynchronize(s));
         uint64_t io = 0;
         for (int k = 0; k <= it_total; k++) io += (k == 0 || k == it_total) ? h[k] : 2ull * h[k];
         ctx->stats.queue_slots_io = io;
+        if (const char *dump = std::getenv("PTB200_DUMP_LAUNCHES")) {      // tuning aid: one line per launch (start in us, phase, live slots)
+            if (FILE *f = std::fopen(dump, "a")) {
+                std::fprintf(f, "# render %dx%d spp %d mode %d: %d launches\n", w, h, p->spp, p->mode, it_total);
+                for (int k = 0; k < n_rec; k++)
+                    std::fprintf(f, "%d %.2f %u %u %u\n", k, (double)(rec[k].t_start - rec[0].t_start) * 1e-3, rec[k].exhausted, rec[k].n_in, h[k + 1]);
+                std::fprintf(f, "resolve %.2f end %.2f\n", (double)(stamps[0] - rec[0].t_start) * 1e-3, (double)(stamps[1] - rec[0].t_start) * 1e-3);
+                std::fclose(f);
+            }
+        }
+        // phases: launches are back to back on one stream, so a launch ends where the next one (or the resolve) starts
+        int first_tail = n_rec;
+        for (int k = 0; k < n_rec; k++) if (rec[k].exhausted) { first_tail = k; break; }
+        const unsigned long long t0 = rec[0].t_start, t_tail = first_tail < n_rec ? rec[first_tail].t_start : stamps[0];
+        ctx->stats.main_kernel_ms = (double)(t_tail - t0) * 1e-6;
+        ctx->stats.tail_ms = (double)(stamps[0] - t_tail) * 1e-6;
+        ctx->stats.resolve_ms = (double)(stamps[1] - stamps[0]) * 1e-6;
+        ctx->stats.tail_launches = (uint64_t)(it_total - std::min(first_tail, it_total));
     }
     return PT_OK;
 }

@@ -153,3 +153,46 @@ class SharedImage:
                 self.ptrs[b] = None
         finally:
             self.ptrs = [None] * self.n_buf
+
+
+class HostImage:
+    """One (H, W, 3) float64 image in POSIX shared memory, mapped by every rank of the node and page-locked for DMA.
+
+    The end-to-end path of a multi-GPU render: each rank copies ITS row tiles device -> host over its own PCIe link
+    (Context.readback_owned) and the picture of src/smallpt.cpp:538 assembles in host memory; nothing funnels through
+    rank 0's GPU.  The only synchronisation is the caller's barrier after the copies."""
+
+    def __init__(self, ctx, height, width, rank, world, dst=0, group=None):
+        import os
+        import torch.distributed as dist
+        self.ctx, self.rank, self.dst = ctx, rank, dst
+        self.shape = (height, width, 3)
+        nbytes = height * width * 3 * 8
+        name = [None]
+        if rank == dst:
+            name[0] = f"/dev/shm/ptb200_img_{os.getpid()}_{id(self) & 0xFFFFFF:x}"
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        if world > 1:
+            dist.broadcast_object_list(name, src=dst, group=group)
+        self.path = name[0]
+        self.array = np.memmap(self.path, dtype=np.float64, mode="r+", shape=self.shape)
+        self.registered = False
+        try:
+            ctx.host_register(self.array)
+            self.registered = True
+        except Exception:               # noqa: BLE001   (pageable memory still works, through the driver's staging buffers)
+            pass
+        if world > 1:
+            dist.barrier(group=group)
+        if rank == dst:
+            os.unlink(self.path)        # the mappings keep the segment alive; nothing is left behind in /dev/shm
+
+    def close(self):
+        if self.array is not None:
+            if self.registered:
+                try:
+                    self.ctx.host_unregister(self.array)
+                except Exception:       # noqa: BLE001
+                    pass
+            self.array = None

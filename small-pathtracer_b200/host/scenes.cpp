@@ -88,6 +88,14 @@ SceneTable scene_B()   // sphere era (src/a.exe static initialiser; SURVEY Appen
     return s;
 }
 
+SceneTable scene_G()   // the sphere-era box with Beason's mirror and glass spheres (ids 7, 8): the SPEC / REFR arms of :481-495
+{
+    SceneTable s = scene_B();
+    s.set_material(7, Vec(1, 1, 1) * .999, SPEC);
+    s.set_material(8, Vec(1, 1, 1) * .999, REFR);
+    return s;
+}
+
 SceneTable scene_C()   // :288-294 + the two spheres of :297-298
 {
     Hitable *rect[] = {
@@ -146,8 +154,9 @@ SceneTable scene_by_name(const std::string &name)
     if (name == "A" || name == "a") return scene_A();
     if (name == "B" || name == "b") return scene_B();
     if (name == "C" || name == "c") return scene_C();
+    if (name == "G" || name == "g") return scene_G();
     if (name == "synthetic" || name == "S" || name == "s" || name == "D") return scene_synthetic();
-    throw std::invalid_argument("unknown scene '" + name + "' (A, B, C, synthetic)");
+    throw std::invalid_argument("unknown scene '" + name + "' (A, B, C, G, synthetic)");
 }
 
 }  // namespace smallpt_b200

@@ -193,6 +193,13 @@ struct SceneTable {
     }
     template <size_t N> void add_all(Hitable *(&table)[N]) { for (size_t i = 0; i < N; i++) add(*table[i]); }
     int size() const { return int(order.size()); }
+    // colour + material of object `id` (scene variants: the mirror / glass spheres of the sphere-era box)
+    void set_material(int id, const Vec &c, Refl_t refl)
+    {
+        const int ref = order.at(size_t(id));
+        if (ref < 0) { pt_sphere &o = spheres[size_t(~ref)]; o.c = c.pod(); o.refl = int(refl); }
+        else { pt_plane &o = planes[size_t(ref)]; o.c = c.pod(); o.refl = int(refl); }
+    }
     // the literals of :365-367,:467,:471
     void set_reference_light(int id = 6, double x0 = 32, double xw = 36, double z0 = 63, double zw = 36,
                              double y = 81.6, double area = 1296)
@@ -212,6 +219,7 @@ struct SceneTable {
 // Built-in scenes -------------------------------------------------------------------------------
 SceneTable scene_A();     // HEAD: 17 rectangles (:287-311)
 SceneTable scene_B();     // sphere era: 10 spheres (recovered from src/a.exe)
+SceneTable scene_G();     // scene B with a mirror (id 7) and a glass (id 8) sphere: SPEC / REFR (:481-495)
 SceneTable scene_C();     // 7 rectangles + the two commented spheres of :297-298 (image_light_test.ppm)
 SceneTable scene_synthetic(int n_spheres = 256, int n_tilted = 8, uint64_t seed = 12345);   // config C4
 SceneTable scene_by_name(const std::string &name);

@@ -157,10 +157,29 @@ def converged():
             print("wrote converged", scene, name, "%.1f s" % (st.render_ms / 1e3), flush=True)
 
 
+def converged_glossy():
+    """Scene G (mirror + glass spheres, the SPEC / REFR arms of src/smallpt.cpp:481-495, with the depth <= 2 split) from the
+    C oracle: converged cosine-mode image + per-pixel sums of squares, for the FP32 engine's 3-sigma and variance gates."""
+    from _pkg import ptb
+    from oracle import pyoracle as orc
+    w = h = 128
+    spp = 4096
+    sc = ptb.builtin_scene("G", w, h)
+    cl, mean, sq, st = orc.oracle_render(sc, ptb.params(w, h, spp, mode=1, engine=1))
+    np.savez_compressed(os.path.join(HERE, "converged_G_cos.npz"), mean=mean.astype(np.float32), sumsq=sq.astype(np.float32),
+                        spp=np.array(spp), rays_per_path=np.array(st.rays / st.paths), miss_per_path=np.array(st.miss_events / st.paths))
+    print("wrote converged G cos", "%.1f s" % (st.render_ms / 1e3), flush=True)
+
+
 if __name__ == "__main__":
+    if "--glossy-only" in sys.argv:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        converged_glossy()
+        sys.exit(0)
     if not (os.path.exists(REF_BIN) and os.path.exists(HARNESS)):
         raise SystemExit("oracle/_ref is not built (needs /root/reference): run `make -C oracle`")
     ref_render()
     ref_units()
     if "--converged" in sys.argv:
         converged()
+        converged_glossy()

@@ -45,8 +45,12 @@ def test_bench_line_on_gpu():
     d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
     assert (BASE_KEYS - {"cpu_baseline"}) | {"clocks", "gpu_launches", "roofline", "mrays_per_s"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["gpu_launches"] > 0
-    assert d["config"]["workload"].startswith("C2") and d["value"] > 1000 and 0 < d["e2e"]["value"] <= d["value"] * 1.02
-    assert d["e2e"]["d2h_bytes_per_step"] == 512 * 512 * 3 * 8 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert d["config"]["workload"].startswith("C5") and d["value"] > 1000 and 0 < d["e2e"]["value"] <= d["value"] * 1.02
+    assert d["scaling"] == "strong"             # the same workload at every N
+    assert d["e2e"]["d2h_bytes_per_step"] == 3840 * 2160 * 3 * 8 and d["e2e"]["h2d_bytes_per_step"] > 0
+    ph = d["phases"]
+    assert ph["generating"]["max_over_ranks_ms"] > 0 and ph["tail"]["max_over_ranks_ms"] >= 0 and ph["resolve"]["max_over_ranks_ms"] > 0
+    assert ph["generating"]["max_over_ranks_ms"] + ph["tail"]["max_over_ranks_ms"] + ph["resolve"]["max_over_ranks_ms"] <= d["ms_per_step"] * 1.01
     rf = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

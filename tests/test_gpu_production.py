@@ -122,8 +122,8 @@ def test_cone_light_sampling_is_unbiased(light):
 
 
 def test_synthetic_scene_matches_oracle_statistics():
-    # 256 spheres + tilted planes + SPEC/REFR, cosine mode: FP32 engine (always-stochastic REFR) vs the FP64
-    # oracle (splits at depth <= 2): same expectation
+    # 256 spheres + tilted planes + SPEC/REFR, cosine mode: FP32 engine (collect_stats: one REFR arm at every depth) vs
+    # the FP64 oracle (splits at depth <= 2): same expectation
     w, h = 48, 36
     sc = ptb.builtin_scene("synthetic", w, h)
     with ptb.Context(sc) as c:
@@ -286,20 +286,50 @@ def test_every_pixel_gets_exactly_spp_samples(spec):
 
 
 @pytest.mark.parametrize("engine", [0, 1], ids=["fp32-philox", "fp64-erand48"])
-def test_reference_fixture_statistics_scene_B(engine):
-    # the reference's own saved renders (512x512 P3 files) pin image means in 8-bit gamma space.
-    # image2_32pps_importancesampl.ppm (scene B, cosine, 32 spp): mean RGB (131.3, 132.8, 109.5);
-    # image_32pps_totalrandom.ppm (scene B, uniform hemisphere with weight 1, 32 spp): (102.6, 104.0, 84.8).
-    # Both GPU engines, through the reference's own output formula: clamp the per-pixel mean, toInt (:314-321, :538).
-    w = h = 512
+@pytest.mark.parametrize("name", ["image1_16ssp_importsampl.ppm", "image2_32pps_importancesampl.ppm", "image_32pps_totalrandom.ppm",
+                                  "image_512pps_explicitlight_test.ppm", "image_light_test.ppm"])
+def test_reference_fixture_statistics(engine, name):
+    # the reference's own saved renders (512x512 P3 files) pin image means in 8-bit gamma space.  Their
+    # statistics are read from the PPMs themselves by tests/golden/make_fixture_stats.py (tests/test_fixture_stats.py
+    # re-derives them when /root/reference is present).  Scene B cosine 16 / 32 spp, scene B uniform with weight 1, and
+    # scene C (rectangle walls + two spheres) with the reference's NEE.  Both GPU engines, through the reference's own
+    # output formula: clamp the per-pixel mean, toInt (:314-321, :538).
+    import json
+    with open(os.path.join(GOLDEN, "fixture_stats.json")) as f:
+        fx = json.load(f)[name]
+    assert fx["pinned"]
+    w, h = fx["width"], fx["height"]
+    sc = ptb.builtin_scene(fx["scene"], w, h)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(w, h, fx["spp"], mode=MODE[fx["mode"]], engine=engine, seed=2))
+        mean, _ = c.readback()
+    ints = np.floor(np.clip(mean, 0.0, 1.0) ** (1 / 2.2) * 255 + .5)
+    got = ints.reshape(-1, 3).mean(axis=0)
+    assert np.all(np.abs(got - np.array(fx["mean_rgb_8bit"])) < 0.75), (engine, name, got, fx["mean_rgb_8bit"])
+    lin = (ints / 255.0) ** 2.2
+    blocks = lin.reshape(h // 32, 32, w // 32, 32, 3).mean(axis=(1, 3))
+    want = np.array(fx["block_means_linear_16x16"])
+    assert np.abs(blocks - want).sum() / want.sum() < 0.08
+
+
+def test_unpinned_explicit_light_fixtures_are_a_loose_sanity_target():
+    # The `*explicit*` fixtures come from a sphere-era light sampler whose source is not in the repository (SURVEY
+    # section 4: "unpinned; use only as a visual sanity target").  Cone sampling toward the sphere light is unbiased, the
+    # lost estimator was not (about 0.75x on directly lit walls): the images agree only loosely - ours is 1.0-2.0x as bright overall (1.56x on the CPU oracle),
+    # and it is the same picture (block means correlate).
+    import json
+    with open(os.path.join(GOLDEN, "fixture_stats.json")) as f:
+        fx = json.load(f)["image_512pps_explicitlight.ppm"]
+    w, h = fx["width"], fx["height"]
     sc = ptb.builtin_scene("B", w, h)
     with ptb.Context(sc) as c:
-        for mode, want in ((1, (131.3, 132.8, 109.5)), (2, (102.6, 104.0, 84.8))):
-            c.render(ptb.params(w, h, 32, mode=mode, engine=engine, seed=2))
-            mean, _ = c.readback()
-            ints = np.floor(np.clip(mean, 0.0, 1.0) ** (1 / 2.2) * 255 + .5)
-            got = ints.reshape(-1, 3).mean(axis=0)
-            assert np.all(np.abs(got - np.array(want)) < 0.75), (engine, mode, got)
+        c.render(ptb.params(w, h, 64, mode=ptb.PT_MODE_NEE_CONE_SPHERE, seed=2))
+        mean, _ = c.readback()
+    lin = (np.floor(np.clip(mean, 0.0, 1.0) ** (1 / 2.2) * 255 + .5) / 255.0) ** 2.2
+    blocks = lin.reshape(h // 32, 32, w // 32, 32, 3).mean(axis=(1, 3))
+    want = np.array(fx["block_means_linear_16x16"])
+    assert 1.0 < blocks.sum() / want.sum() < 2.0
+    assert np.corrcoef(blocks.ravel(), want.ravel())[0, 1] > 0.9
 
 
 def _shelf_scene(n_shelves, w, h):
@@ -415,7 +445,8 @@ def test_full_size_c4_properties():
     assert out[0][1:5] == out[1][1:5] and out[0][1] == w * h * spp
     assert np.array_equal(out[0][0], out[1][0])
     assert np.isfinite(out[0][0]).all() and (out[0][0] >= 0).all()
-    assert 7.5 < out[0][2] / out[0][1] < 9.5          # rays per path of the cosine estimator on this scene (8.4)
+    # rays per path of the cosine estimator on this scene: 9.53 in the oracle (8.4 before the depth <= 2 REFR split, :494-495)
+    assert 9.0 < out[0][2] / out[0][1] < 10.0
 
 
 def test_scene_replacement_grows_tables_safely():
