@@ -138,7 +138,11 @@ typedef struct pt_render_params {
      * of the target untouched, so that all ranks can render straight into ONE image — rank 0's buffer, opened by the
      * other processes through pt_ipc_open and written over NVLink peer memory by the resolve kernel. */
     int      owned_rows_only;
-    int      _pad;
+    /* NOT the reference's behaviour (default 0).  The reference's rectangles have no epsilon (src/smallpt.cpp:106): a
+     * bounce that starts an ulp behind its own rectangle hits it again at a tiny t and leaks out of the box (SURVEY
+     * Appendix C #2; 0.03-0.5 miss events per path).  robust_eps = 1 makes the FP32 engine's rectangles require
+     * t > 1e-4 like its spheres do, which removes those leaks (and the energy they lose). */
+    int      robust_eps;
 } pt_render_params;
 
 typedef struct pt_stats {

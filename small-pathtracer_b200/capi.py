@@ -59,7 +59,7 @@ class RenderParams(C.Structure):
                 ("engine", C.c_int), ("sincos", C.c_int), ("seed", C.c_uint64),
                 ("tile_rows", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("max_depth", C.c_int),
                 ("queue_capacity", C.c_int), ("collect_stats", C.c_int), ("bounces_per_launch", C.c_int),
-                ("sample_offset", C.c_int), ("accumulate", C.c_int), ("owned_rows_only", C.c_int), ("_pad", C.c_int)]
+                ("sample_offset", C.c_int), ("accumulate", C.c_int), ("owned_rows_only", C.c_int), ("robust_eps", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -260,12 +260,12 @@ def write_ppm(path, rgb_mean, w, h):
 
 def params(w, h, spp, mode=PT_MODE_NEE_REF_RECT, engine=PT_ENGINE_FP32_PHILOX, sincos=PT_SINCOS_LIBM, seed=0,
            tile_rows=0, rank=0, world=1, max_depth=0, queue_capacity=0, collect_stats=0, bounces_per_launch=0,
-           sample_offset=0, accumulate=0, owned_rows_only=0):
+           sample_offset=0, accumulate=0, owned_rows_only=0, robust_eps=0):
     p = RenderParams()
     p.width, p.height, p.spp, p.mode, p.engine, p.sincos, p.seed = w, h, spp, mode, engine, sincos, seed
     p.tile_rows, p.rank, p.world, p.max_depth = tile_rows, rank, world, max_depth
     p.queue_capacity, p.collect_stats, p.bounces_per_launch = queue_capacity, collect_stats, bounces_per_launch
-    p.sample_offset, p.accumulate, p.owned_rows_only = sample_offset, accumulate, owned_rows_only
+    p.sample_offset, p.accumulate, p.owned_rows_only, p.robust_eps = sample_offset, accumulate, owned_rows_only, robust_eps
     return p
 
 

@@ -125,6 +125,31 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
         for (int k = S.n_sph; k < S.n_sph4; k++) S.sphf[k] = make_float4(0.f, 0.f, 0.f, 3.0e38f);
         S.sph_kM2 = (float)(PT_SPH_KAPPA * M2);
     }
+    {   // re-centred form of the huge spheres: with w = o - huge_c (small) and G = centre - huge_c,
+        //   |o - centre|^2 - rad^2 = |w|^2 - 2 w.G + (|G|^2 - rad^2): the constant K = |G|^2 - rad^2 is formed in FP64 here
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        int n_near = 0;
+        for (int i = 0; i < n; i++) {
+            const DevObj64 &o = ctx->objs[i];
+            double q[3];
+            if (o.type == OT_SPHERE) { if (o.g[0] >= PT_HUGE_RADIUS) continue; q[0] = o.g[1]; q[1] = o.g[2]; q[2] = o.g[3]; }
+            else if (o.type == OT_TILT) { q[0] = o.p0[0]; q[1] = o.p0[1]; q[2] = o.p0[2]; }
+            else {      // rectangle centre: (a, b, k) in the axis order of its class
+                const double ca = 0.5 * (o.g[0] + o.g[1]), cb = 0.5 * (o.g[2] + o.g[3]), k = o.g[4];
+                if (o.type == OT_XZ) { q[0] = ca; q[1] = k; q[2] = cb; } else if (o.type == OT_XY) { q[0] = ca; q[1] = cb; q[2] = k; } else { q[0] = k; q[1] = ca; q[2] = cb; }
+            }
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], q[a]); hi[a] = std::fmax(hi[a], q[a]); }
+            n_near++;
+        }
+        const double cam[3] = {ctx->cam.origin.x, ctx->cam.origin.y, ctx->cam.origin.z};
+        for (int a = 0; a < 3; a++) S.huge_c[a] = (float)(n_near ? 0.5 * (lo[a] + hi[a]) : cam[a]);
+        for (int k = 0; k < S.n_huge; k++) {
+            double G[3], K = -S.huge[k][3];
+            for (int a = 0; a < 3; a++) { G[a] = S.huge[k][a] - (double)S.huge_c[a]; K += G[a] * G[a]; }
+            for (int a = 0; a < 3; a++) { S.hugeg[k][a] = (float)G[a]; S.hugeg[k][3 + a] = (float)(G[a] - (double)S.hugeg[k][a]); }
+            S.hugeg[k][6] = (float)K; S.hugeg[k][7] = (float)(K - (double)S.hugeg[k][6]);
+        }
+    }
     for (int i = 0; i < n; i++) S.refl_mask |= 1 << ctx->objs[i].refl;
     S.code_obj0 = code_of[0];
     S.light_code = (ctx->light.id >= 0 && ctx->light.id < n) ? code_of[ctx->light.id] : -2;
@@ -301,6 +326,8 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     if (p->sample_offset < 0) return pt_fail(ctx, PT_ERR_ARG, "sample_offset must be >= 0");
     if (p->accumulate && p->engine != PT_ENGINE_FP32_PHILOX)
         return pt_fail(ctx, PT_ERR_ARG, "accumulate = 1 is an FP32 engine feature (the erand48 replay consumes one sequential stream per row)");
+    if (p->robust_eps && p->engine != PT_ENGINE_FP32_PHILOX)
+        return pt_fail(ctx, PT_ERR_ARG, "robust_eps is an FP32 engine option (the FP64 engine replays the reference, which has no epsilon on rectangles)");
     if (p->mode < PT_MODE_NEE_REF_RECT || p->mode > PT_MODE_NEE_CONE_SPHERE) return pt_fail(ctx, PT_ERR_ARG, "bad mode");
     if (p->engine != PT_ENGINE_FP32_PHILOX && p->engine != PT_ENGINE_FP64_ERAND48) return pt_fail(ctx, PT_ERR_ARG, "bad engine");
     const int world = p->world > 0 ? p->world : 1;

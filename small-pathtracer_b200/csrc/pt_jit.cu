@@ -192,6 +192,14 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
             h += b;
         }
         h += "};\n";
+        std::snprintf(b, sizeof b, "constexpr float PT_J_HUGEG[%d][8] = {\n", S.n_huge);      // the re-centred FP32 form
+        h += b;
+        for (int k = 0; k < S.n_huge; k++) {
+            h += " {";
+            for (int a = 0; a < 8; a++) { put_float(h, S.hugeg[k][a]); h += ","; }
+            h += "},\n";
+        }
+        h += "};\nconstexpr float PT_J_huge_c[3] = {"; put_float(h, S.huge_c[0]); h += ","; put_float(h, S.huge_c[1]); h += ","; put_float(h, S.huge_c[2]); h += "};\n";
     }
     h += "constexpr float PT_J_sph_c[3] = {"; put_float(h, S.sph_c[0]); h += ","; put_float(h, S.sph_c[1]); h += ","; put_float(h, S.sph_c[2]); h += "};\n";
     return h;

@@ -54,8 +54,12 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     float  sph_kM2;               // PT_SPH_KAPPA * max_i (|c'_i| + rad_i)^2
     int    n_sph4;                // n_sph rounded up to a multiple of 4
     int    refl_mask;             // bit r set: some object has material r (PT_DIFF / PT_SPEC / PT_REFR)
-    double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64
+    double huge[PT_MAX_HUGE][4];  // c.x, c.y, c.z, rad^2 in FP64 (the FP64 c-term of round 1: -DPT_HUGE_FP64)
     float  hugef[PT_MAX_HUGE][4]; // the same centres rounded to FP32 (for b = (c - o).d)
+    // re-centred FP32 form of the same spheres (see closest_hit): G = centre - huge_c and K = |G|^2 - rad^2, each as a
+    // two-float (hi + lo): {G_hi.xyz, G_lo.xyz, K_hi, K_lo}
+    float  hugeg[PT_MAX_HUGE][8];
+    float  huge_c[3];             // reference point near the rays' origins (centre of the non-huge objects)
     float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
 };
 

@@ -249,6 +249,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
         P.use_magic = (owned_pixels < (1ull << 24) && w < 65536 && tile < 65536) ? 1 : 0;
         P.key_low = PT_KEY_CODE_BITS;
+        P.rect_tmin = p->robust_eps ? PT_EPS_F : 1.401298464e-45f;      // reference: no epsilon on rectangles (:106)
         P.wrap_once = owned_pixels >= 32ull ? 1 : 0;
         P.max_depth = p->max_depth > 0 ? p->max_depth : 4096;
         if (P.max_depth > 65000) P.max_depth = 65000;
@@ -285,6 +286,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
                 P.n_in = n_it + it; P.n_out = n_it + it + 1;
                 P.first_launch = it == 0 ? 1 : 0;
                 P.launch_rec = ctx->d_launch_rec + std::min(it, PT_MAX_LAUNCH_RECS - 1);
+                P.launch_rec0 = ctx->d_launch_rec;
                 switch (p->mode) {
                 case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, glossy, blocks, s, P, jk); break;
                 case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, glossy, blocks, s, P, jk); break;

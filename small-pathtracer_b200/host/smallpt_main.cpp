@@ -4,6 +4,8 @@
 //                             [--ppm6 file] [--pfm file] [--raw64 file] [--variance file] [--dump-scene file]
 //                             [--chunk N] [--checkpoint file] [--resume file]      progressive accumulation
 //                             [--gpus N]                                           row tiles over N GPUs of this node
+//                             [--robust-eps]            NOT the reference: rectangles require t > 1e-4 (no self-hit leaks)
+//                             [--stats]                 print why paths ended and the live-path histogram (slower render)
 // `spp` is argv[1] as the north star asks (the reference hard-codes samps = 16 at :508).
 #include <algorithm>
 #include <chrono>
@@ -21,7 +23,7 @@ int main(int argc, char *argv[])
     int samps = 16;                // :508
     std::string mode = "nee", scene_name = "A", out = "image.ppm", scene_file, ppm6, pfm, raw64, variance, dump_scene, checkpoint, resume;
     int chunk = 0, gpus = 1;
-    bool validate = false, det = false;
+    bool validate = false, det = false, robust = false, want_stats = false;
     uint64_t seed = 0;
     int argi = 1;
     if (argc > 1 && argv[1][0] != '-') { samps = std::atoi(argv[1]); argi = 2; }
@@ -36,6 +38,8 @@ int main(int argc, char *argv[])
         else if (a == "--size") { if (std::sscanf(need("--size"), "%dx%d", &w, &h) != 2) { std::cerr << "--size WxH\n"; return 2; } }
         else if (a == "--validate") validate = true;
         else if (a == "--det-sincos") det = true;
+        else if (a == "--robust-eps") robust = true;
+        else if (a == "--stats") want_stats = true;
         else if (a == "--seed") seed = std::strtoull(need("--seed"), nullptr, 10);
         else if (a == "--out") out = need("--out");
         else if (a == "--scene-file") scene_file = need("--scene-file");
@@ -57,7 +61,8 @@ int main(int argc, char *argv[])
     p.engine = validate ? PT_ENGINE_FP64_ERAND48 : PT_ENGINE_FP32_PHILOX;
     p.sincos = det ? PT_SINCOS_DET : PT_SINCOS_LIBM;
     p.world = 1;
-    p.collect_stats = variance.empty() ? 0 : 1;
+    p.collect_stats = (variance.empty() && !want_stats) ? 0 : 1;
+    p.robust_eps = robust ? 1 : 0;
     try {
         auto t1 = std::chrono::high_resolution_clock::now();
         SceneTable scene;
@@ -75,15 +80,15 @@ int main(int argc, char *argv[])
             o << scene_to_text(scene, cam_spec);
         }
         Camera cam = cam_spec.make(w, h);                                              // :521
-        if (gpus > 1 && (validate || chunk > 0 || !resume.empty() || !checkpoint.empty() || !variance.empty())) {
+        if (gpus > 1 && (validate || chunk > 0 || !resume.empty() || !checkpoint.empty() || p.collect_stats)) {
             std::cerr << "--gpus N combines with the plain FP32 render only\n";
             return 2;
         }
         Renderer r(scene, cam, -1, gpus);
         // Progressive accumulation: the sample range [0, samps) in chunks; every chunk continues the same image (samples are
         // Philox streams keyed by their index), a checkpoint holds the per-pixel sums and the number of samples in them.
-        if ((chunk > 0 || !resume.empty() || !checkpoint.empty()) && (validate || !variance.empty())) {
-            std::cerr << "--chunk/--checkpoint/--resume apply to the FP32 engine without --variance\n";
+        if ((chunk > 0 || !resume.empty() || !checkpoint.empty()) && (validate || p.collect_stats)) {
+            std::cerr << "--chunk/--checkpoint/--resume apply to the FP32 engine without --variance / --stats\n";
             return 2;
         }
         int done = 0;
@@ -114,7 +119,7 @@ int main(int argc, char *argv[])
             }
         }
         std::vector<double> sumsq;
-        std::vector<double> c = r.readback(w, h, &st, variance.empty() ? nullptr : &sumsq);
+        std::vector<double> c = r.readback(w, h, &st, p.collect_stats ? &sumsq : nullptr);
         if (render_ms > 0) { st.render_ms = render_ms; st.paths = paths; st.rays_camera = rays_c; st.rays_scatter = rays_s; st.rays_shadow = rays_sh; }
         write_ppm(out, c.data(), w, h);                                                // :548-551
         if (!ppm6.empty()) write_ppm_binary(ppm6, c.data(), w, h);
@@ -126,6 +131,13 @@ int main(int argc, char *argv[])
         std::cout << "PATHS: " << st.paths << "  RAYS: " << (uint64_t)rays << "  MAX DEPTH: " << st.max_depth_seen << std::endl;
         std::cout << "RENDER ms: " << st.render_ms << "  Mpaths/s: " << st.paths / st.render_ms * 1e-3
                   << "  Mrays/s: " << rays / st.render_ms * 1e-3 << std::endl;
+        if (want_stats && !validate) {
+            std::cout << "ENDED BY: roulette " << st.term_roulette << "  emitter " << st.term_emitter << "  light sample " << st.term_light_sample
+                      << "  max depth " << st.truncated << "  | MISSES: " << st.miss_events << "  DROPPED CONTRIBUTIONS: " << st.dropped_contributions << std::endl;
+            std::cout << "LIVE PATHS BY DEPTH:";
+            for (int k = 0; k < 64 && st.live_at_depth[k]; k++) std::cout << " " << st.live_at_depth[k];
+            std::cout << std::endl;
+        }
         std::cout << " DURATION : " << std::chrono::duration_cast<std::chrono::milliseconds>(t2 - t1).count();   // :554-556
         std::cout << std::endl;
     } catch (const std::exception &e) {

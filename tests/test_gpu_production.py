@@ -488,3 +488,38 @@ def test_owned_rows_only_rejects_statistics():
                 c.render_into(ptb.params(w, h, 4, mode=0, world=2, rank=0, owned_rows_only=1, collect_stats=1), buf)
         finally:
             c.device_free(buf)
+
+
+def test_robust_eps_option_removes_the_self_hit_leaks():
+    # The reference's rectangles have no epsilon (:106): a bounce that starts an ulp behind its own rectangle hits it again
+    # at a tiny t and scatters out of the box.  The default keeps that behaviour (parity); the
+    # non-default robust_eps = 1 requires t > 1e-4 on rectangles too.  It is an FP32 engine option.
+    w = h = 128
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        out = {}
+        for mode in (0, 1):
+            for robust in (0, 1):
+                c.render(ptb.params(w, h, 64, mode=mode, seed=9, robust_eps=robust))
+                img, st = c.readback()
+                out[(mode, robust)] = (st.miss_events / st.paths, img.mean(), st.paths)
+        with pytest.raises(ptb.PtError, match="robust_eps"):
+            c.render(ptb.params(w, h, 1, mode=0, engine=ptb.PT_ENGINE_FP64_ERAND48, robust_eps=1))
+    assert out[(0, 0)][0] > 0.02 and out[(1, 0)][0] > 0.2            # the reference's leak rates (0.03 / 0.42 per path in FP64)
+    assert out[(0, 1)][0] < 0.002 and out[(1, 1)][0] < 0.01          # gone
+    assert out[(1, 1)][1] > out[(1, 0)][1]                           # the leaked paths no longer lose their energy
+
+
+@pytest.mark.parametrize("scene,mode", [("A", 0), ("A", 1), ("B", 2), ("G", 1), ("B", 3)])
+def test_termination_statistics_add_up(scene, mode):
+    # collect_stats = 1: every path ends exactly one way, and the live-path histogram counts every shaded vertex
+    w, h, spp = 96, 64, 32
+    sc = ptb.builtin_scene(scene, w, h)
+    with ptb.Context(sc) as c:
+        c.render(ptb.params(w, h, spp, mode=mode, seed=3, collect_stats=1, max_depth=40))
+        _, st = c.readback()
+    hist = np.array(list(st.live_at_depth), dtype=np.int64)
+    assert st.term_roulette + st.term_emitter + st.term_light_sample + st.truncated == st.paths == w * h * spp
+    assert hist.sum() == st.shaded_vertices and hist[0] == st.paths
+    assert (np.diff(hist[:40]) <= 0).all() and st.dropped_contributions == 0
+    assert (st.term_light_sample > 0) == (mode == 0) and st.term_emitter > 0 and st.truncated > 0

@@ -15,7 +15,7 @@ __device__ __forceinline__ unsigned long long pack2(float a, float b)
 }
 
 template <int OP>
-__global__ void k(float *out, float seed, long long *cycles)
+__global__ void __launch_bounds__(1024, 1) k(float *out, float seed, long long *cycles)
 {
     float a[CH], b[CH], c[CH];
     unsigned long long A[CH], B[CH], Cc[CH];
@@ -65,9 +65,15 @@ __global__ void k(float *out, float seed, long long *cycles)
                 A[i] = WU;
             }
             if (OP == 10) {  // sphere scan, scalar: 7 FFMA (one immediate operand each), FSETP, @p LOP (9 instructions)
-                const float bb = fmaf(1.25f + i, a[0], fmaf(2.5f + i, a[1], fmaf(-3.75f + i, a[2], -a[3])));
-                const float cc = fmaf(1.25f + i, b[0], fmaf(2.5f + i, b[1], fmaf(-3.75f + i, b[2], b[3])));
-                asm volatile("{.reg .pred p; setp.ge.f32 p, %1, 0f42C80000; @p or.b32 %0, %0, %2;}" : "+r"(key) : "f"(fmaf(bb, bb, -cc)), "r"(1u << i));
+                float bb, cc, dd;      // (asm volatile: the loop-invariant operands must not be hoisted)
+                asm volatile("fma.rn.f32 %0, %1, 0f3FA00000, %2;" : "=f"(bb) : "f"(a[0]), "f"(a[3]));
+                asm volatile("fma.rn.f32 %0, %1, 0f40200000, %0;" : "+f"(bb) : "f"(a[1]));
+                asm volatile("fma.rn.f32 %0, %1, 0fC0700000, %0;" : "+f"(bb) : "f"(a[2]));
+                asm volatile("fma.rn.f32 %0, %1, 0f3FA00000, %2;" : "=f"(cc) : "f"(b[0]), "f"(b[3]));
+                asm volatile("fma.rn.f32 %0, %1, 0f40200000, %0;" : "+f"(cc) : "f"(b[1]));
+                asm volatile("fma.rn.f32 %0, %1, 0fC0700000, %0;" : "+f"(cc) : "f"(b[2]));
+                asm volatile("fma.rn.f32 %0, %1, %1, %2;" : "=f"(dd) : "f"(bb), "f"(cc));
+                asm volatile("{.reg .pred p; setp.ge.f32 p, %1, 0f42C80000; @p or.b32 %0, %0, %2;}" : "+r"(key) : "f"(dd), "r"(1u << i));
             }
             if (OP == 11 && (i & 1) == 0) {  // sphere scan, two spheres per packed op: 7 FFMA2 + 2 x (FSETP, @p LOP) = 11 for two (table pairs in registers)
                 unsigned long long BB, CC, D;
