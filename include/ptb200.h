@@ -90,7 +90,7 @@ typedef struct pt_scene {
     pt_light         light;
 } pt_scene;
 
-#define PT_MAX_OBJECTS 1024
+#define PT_MAX_OBJECTS 16000
 
 /* Integrators.  COS / UNI = src/smallpt.cpp:474-477 arm with the cosine (:337-348) or
  * uniform (:351-360, weight 1 — no 2cos factor, as in the reference) sampler;
@@ -124,7 +124,7 @@ typedef struct pt_render_params {
      * rank=0, world=1 renders the whole image.  Pixels of foreign tiles stay zero. */
     int      tile_rows;       /* 0 = default (8) */
     int      rank, world;
-    int      max_depth;       /* safety cap on path length; 0 = default (4096) */
+    int      max_depth;       /* safety cap on path length; 0 = default (4096); at most 8000 */
     int      queue_capacity;  /* wavefront queue slots; 0 = default (sized to L2) */
     int      collect_stats;   /* 1 = also accumulate per-pixel sum of squares */
     int      bounces_per_launch; /* FP32 engine: bounces a path slot advances per kernel launch; 0 = default (512) */
@@ -173,6 +173,8 @@ typedef struct pt_stats {
     uint64_t dropped_contributions; /* radiance contributions that were NaN, negative or clamped (>= 6e10): not added  */
     uint64_t spawned_branches;  /* second REFR branches spawned while depth <= 2 (:494-495)                             */
     uint64_t live_at_depth[64]; /* [d] = paths that shaded a vertex at depth d+1 (last bucket: depth >= 64)             */
+    uint64_t split_refusals;    /* REFR vertices at depth <= 2 that took one arm because their warp's stack was full (expected: 0) */
+    uint64_t accel_structure;   /* 0 = brute force over every primitive; 1 = uniform grid over the small spheres (pt_set_acceleration) */
 } pt_stats;
 
 typedef enum pt_status {
@@ -284,6 +286,15 @@ int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
  * The two builds perform the same operations in the same order (bit-identical images), so which one ran shows only
  * in pt_stats.specialised and in the time. */
 int pt_set_specialisation(pt_ctx *ctx, int mode);
+
+/* Acceleration structure of the FP32 engine for scenes beyond brute force.  The measured contract stays the
+ * brute-force loop of src/smallpt.cpp:323-335 (every primitive, every ray): up to 512 small spheres are scanned that way.
+ * mode: 0 = brute force only (a scene with more than 512 small spheres is refused by the FP32 engine);
+ *       1 (default) = a uniform grid over the small spheres when there are more than 512 of them;
+ *       2 = always the grid (test mode: the same ids, t and images as brute force on scenes that fit both).
+ * Rectangles, huge spheres and tilted planes are always tested one by one.  The FP64 engine is always brute force (it is
+ * what the grid's hit ids are checked against).  Takes effect at the next pt_scene_upload. */
+int pt_set_acceleration(pt_ctx *ctx, int mode);
 
 /* The context's statistics record as it stands (pt_readback needs a finished render; the debug entries only set
  * `specialised`). Test entry. */

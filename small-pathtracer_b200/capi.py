@@ -70,7 +70,8 @@ class Stats(C.Structure):
                 ("render_ms", C.c_double), ("main_kernel_ms", C.c_double), ("queue_slots_io", C.c_uint64),
                 ("tail_ms", C.c_double), ("resolve_ms", C.c_double), ("tail_launches", C.c_uint64),
                 ("term_roulette", C.c_uint64), ("term_emitter", C.c_uint64), ("term_light_sample", C.c_uint64),
-                ("dropped_contributions", C.c_uint64), ("spawned_branches", C.c_uint64), ("live_at_depth", C.c_uint64 * 64)]
+                ("dropped_contributions", C.c_uint64), ("spawned_branches", C.c_uint64), ("live_at_depth", C.c_uint64 * 64),
+                ("split_refusals", C.c_uint64), ("accel_structure", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "live_at_depth" else getattr(self, n)) for n, _ in self._fields_ if not n.startswith("_")}
@@ -274,7 +275,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_readback_owned", "pt_host_register", "pt_host_unregister", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_ffma_peak",
-           "pt_set_specialisation", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_set_acceleration", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -309,6 +310,7 @@ def lib():
         L.pt_debug_philox.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
         L.pt_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pt_set_specialisation.argtypes = [vp, C.c_int]
+        L.pt_set_acceleration.argtypes = [vp, C.c_int]
         L.pt_debug_stats.argtypes = [vp, C.POINTER(Stats)]
         L.pt_debug_specialise.argtypes = [C.POINTER(SceneDesc), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
         L.pt_destroy.argtypes = [vp]
@@ -372,6 +374,11 @@ class Context:
     def set_specialisation(self, mode):
         """0 = generic kernel, 1 = scene-specialised (NVRTC) kernel for big renders (default), 2 = always."""
         self._check(lib().pt_set_specialisation(self._h, mode), "pt_set_specialisation")
+
+    def set_acceleration(self, mode):
+        """0 = brute force only, 1 = uniform grid beyond 512 small spheres (default), 2 = always the grid.  Re-uploads the scene."""
+        self._check(lib().pt_set_acceleration(self._h, mode), "pt_set_acceleration")
+        self.update_scene(self.scene)
 
     def render(self, p):
         self.last = p

@@ -35,7 +35,8 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
     ctx->fp32_ok = true;
     ctx->fp32_why.clear();
     mats.clear();
-    if (n > PT_MAX_OBJ) { ctx->fp32_ok = false; ctx->fp32_why = "more than 512 objects"; return; }
+    ctx->grid.n = 0;
+    ctx->h_grid_start.clear(); ctx->h_grid_items.clear(); ctx->h_grid_sph.clear();
     std::vector<int> code_of(n, -1);
     // rectangles: the first PT_RECT_SLOTS of each axis class go to the unrolled slots, the rest to the overflow loop
     int n_ovf = 0;
@@ -58,8 +59,10 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
                 code_of[i] = axis * PT_RECT_SLOTS + k;
                 k++;
             } else {
-                S.rect_a[n_ovf] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
-                S.rect_b2[n_ovf] = (float)o.g[3];
+                if (n_ovf < PT_MAX_OBJ) {
+                    S.rect_a[n_ovf] = make_float4((float)o.g[4], (float)o.g[0], (float)o.g[1], (float)o.g[2]);
+                    S.rect_b2[n_ovf] = (float)o.g[3];
+                }
                 code_of[i] = 3 * PT_RECT_SLOTS + n_ovf;
                 n_ovf++;
             }
@@ -73,10 +76,14 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
         if (o.type == OT_SPHERE) { if (o.g[0] >= PT_HUGE_RADIUS) n_huge++; else n_small++; }
         else if (o.type == OT_TILT) n_tilt++;
     }
+    // small spheres: brute force (the measured contract) up to PT_MAX_OBJ, beyond that - or on request - a uniform grid
+    const bool use_grid = n_small > 0 && (ctx->accel_mode == 2 || (ctx->accel_mode == 1 && n_small > PT_MAX_OBJ));
+    if (n_small > PT_MAX_OBJ && !use_grid) { ctx->fp32_ok = false; ctx->fp32_why = "more than 512 small spheres (brute force); pt_set_acceleration(ctx, 1) enables the uniform grid"; return; }
+    if (n_ovf > PT_MAX_OBJ) { ctx->fp32_ok = false; ctx->fp32_why = "more than 512 rectangles beyond the 48 unrolled slots"; return; }
     if (n_huge > PT_MAX_HUGE) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 huge spheres"; return; }
     if (n_tilt > PT_MAX_TILT) { ctx->fp32_ok = false; ctx->fp32_why = "more than 64 tilted planes"; return; }
     S.code_sph0 = 3 * PT_RECT_SLOTS + n_ovf;
-    S.code_huge0 = S.code_sph0 + n_small;
+    S.code_huge0 = S.code_sph0 + n_small;      // (grid or scan: sphere k of the class has code code_sph0 + k either way)
     S.code_tilt0 = S.code_huge0 + n_huge;
     S.n_codes = S.code_tilt0 + n_tilt;
     for (int i = 0; i < n; i++) {
@@ -87,6 +94,9 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
                 h[0] = o.g[1]; h[1] = o.g[2]; h[2] = o.g[3]; h[3] = o.g[0] * o.g[0];
                 for (int a = 0; a < 3; a++) S.hugef[S.n_huge][a] = (float)h[a];
                 code_of[i] = S.code_huge0 + S.n_huge++;
+            } else if (use_grid) {      // grid: the sphere table lives in global memory, the constant-memory scan tables stay empty
+                code_of[i] = S.code_sph0 + (int)ctx->h_grid_sph.size();
+                ctx->h_grid_sph.push_back(make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(o.g[0] * o.g[0])));
             } else {
                 S.sph[S.n_sph] = make_float4((float)o.g[1], (float)o.g[2], (float)o.g[3], (float)(o.g[0] * o.g[0]));
                 code_of[i] = S.code_sph0 + S.n_sph++;
@@ -101,6 +111,53 @@ static void build_scene_f32(pt_ctx *ctx, std::vector<MatF32> &mats)
             t[3] = make_float4((float)o.hs, (float)o.ht, 0.f, 0.f);
             code_of[i] = S.code_tilt0 + S.n_tilt++;
         }
+    }
+    if (use_grid) {
+        // Uniform grid over the bounding box of the small spheres, about 4 cells per sphere; a sphere is listed in every cell its
+        // bounding box touches (slightly padded: the traversal works in FP32).  CSR layout, indices ascending within a cell.
+        const std::vector<float4> &sp = ctx->h_grid_sph;
+        const int ns = (int)sp.size();
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (const float4 &q : sp) {
+            const double r = std::sqrt((double)q.w), c[3] = {q.x, q.y, q.z};
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], c[a] - r); hi[a] = std::fmax(hi[a], c[a] + r); }
+        }
+        double ext[3], vol = 1;
+        for (int a = 0; a < 3; a++) { const double pad = 1e-3 * (hi[a] - lo[a]) + 1e-3; lo[a] -= pad; hi[a] += pad; ext[a] = hi[a] - lo[a]; vol *= ext[a]; }
+        const double per = std::cbrt(4.0 * ns / vol);
+        GridDev &G = ctx->grid;
+        size_t ncell = 1;
+        for (int a = 0; a < 3; a++) {
+            G.res[a] = (int)std::fmin(128.0, std::fmax(1.0, std::floor(ext[a] * per + 0.5)));
+            G.lo[a] = (float)lo[a]; G.cell[a] = (float)(ext[a] / G.res[a]); G.inv_cell[a] = (float)(G.res[a] / ext[a]);
+            ncell *= (size_t)G.res[a];
+        }
+        auto cell_range = [&](const float4 &q, int a, int &c0, int &c1) {
+            const double r = std::sqrt((double)q.w) * (1.0 + 1e-5) + 1e-4, c = a == 0 ? q.x : a == 1 ? q.y : q.z;
+            c0 = (int)std::floor((c - r - lo[a]) / ext[a] * G.res[a]); c1 = (int)std::floor((c + r - lo[a]) / ext[a] * G.res[a]);
+            c0 = std::max(0, std::min(G.res[a] - 1, c0)); c1 = std::max(0, std::min(G.res[a] - 1, c1));
+        };
+        std::vector<unsigned int> &start = ctx->h_grid_start, &items = ctx->h_grid_items;
+        start.assign(ncell + 1, 0u);
+        for (int pass = 0; pass < 2; pass++) {
+            for (int k = 0; k < ns; k++) {                       // ascending k: items of a cell come out ascending
+                int x0, x1, y0, y1, z0, z1;
+                cell_range(sp[k], 0, x0, x1); cell_range(sp[k], 1, y0, y1); cell_range(sp[k], 2, z0, z1);
+                for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+                    const size_t cidx = ((size_t)z * G.res[1] + y) * G.res[0] + x;
+                    if (pass == 0) start[cidx + 1]++;
+                    else items[start[cidx]++] = (unsigned int)k;
+                }
+            }
+            if (pass == 0) {
+                for (size_t i = 0; i < ncell; i++) start[i + 1] += start[i];
+                items.resize(start[ncell]);
+            } else {                                             // the fill advanced every start to its end: shift back
+                for (size_t i = ncell; i > 0; i--) start[i] = start[i - 1];
+                start[0] = 0u;
+            }
+        }
+        G.n = ns;
     }
     {   // conservative scan form of the small spheres: translate so the cloud of centres is centred on the origin
         // (smaller magnitudes => smaller FP32 cancellation error in b = c'.d - o'.d and c = |c'|^2 - r^2 - 2 c'.o' + |o'|^2)
@@ -241,6 +298,24 @@ static int upload_tables(pt_ctx *ctx)
             ctx->n_codes_alloc = nc;
         }
         PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_mats, mats.data(), sizeof(MatF32) * nc, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->grid.n > 0) {          // the grid's three arrays (grown, never shrunk)
+            auto grow = [&](void **ptr, size_t &cap, size_t need_bytes) -> cudaError_t {
+                if (cap >= need_bytes) return cudaSuccess;
+                if (*ptr) cudaFree(*ptr);
+                *ptr = nullptr; cap = 0;
+                cudaError_t e = cudaMalloc(ptr, need_bytes);
+                if (e == cudaSuccess) cap = need_bytes;
+                return e;
+            };
+            PT_CUDA(ctx, grow((void **)&ctx->d_grid_start, ctx->grid_start_cap, ctx->h_grid_start.size() * sizeof(unsigned int)));
+            PT_CUDA(ctx, grow((void **)&ctx->d_grid_items, ctx->grid_items_cap, std::max<size_t>(1, ctx->h_grid_items.size()) * sizeof(unsigned int)));
+            PT_CUDA(ctx, grow((void **)&ctx->d_grid_sph, ctx->grid_sph_cap, ctx->h_grid_sph.size() * sizeof(float4)));
+            PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_start, ctx->h_grid_start.data(), ctx->h_grid_start.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+            if (!ctx->h_grid_items.empty())
+                PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_items, ctx->h_grid_items.data(), ctx->h_grid_items.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+            PT_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid_sph, ctx->h_grid_sph.data(), ctx->h_grid_sph.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->grid.start = ctx->d_grid_start; ctx->grid.items = ctx->d_grid_items; ctx->grid.sph = ctx->d_grid_sph;
+        }
         // global-memory mirror of the sphere scan table: k_bounce stages it in shared memory
         if (!ctx->d_sphf) PT_CUDA(ctx, cudaMalloc(&ctx->d_sphf, 2 * sizeof(float4) * (PT_MAX_OBJ + 4)));
         if (ctx->h_scene32->n_sph4 > 0) {
@@ -259,7 +334,7 @@ int pt_scene_upload(pt_ctx **out, const pt_scene *scene, int device)
     pt_ctx *reuse = *out;            // non-NULL: replace the scene of an existing context, keep its device buffers
     const int n = scene->n_spheres + scene->n_planes;
     if (scene->n_spheres < 0 || scene->n_planes < 0) return pt_fail(reuse, PT_ERR_ARG, "negative object count");
-    if (n <= 0 || n > PT_MAX_OBJECTS) return pt_fail(reuse, PT_ERR_ARG, "object count must be in 1..1024");
+    if (n <= 0 || n > PT_MAX_OBJECTS) return pt_fail(reuse, PT_ERR_ARG, "object count must be in 1..16000");
     std::vector<DevObj64> objs;
     std::string why;
     if (flatten_scene(scene, objs, why) != PT_OK) return pt_fail(reuse, PT_ERR_ARG, why);
@@ -359,7 +434,7 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     ctx->last = *p;
     ctx->rendered = false;
     ctx->jit = nullptr;
-    if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode > 0) {
+    if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode > 0 && ctx->grid.n == 0) {      // (grid scenes run the ahead-of-time build)
         // scene-specialised kernel: built (once per scene/mode) BEFORE the timed region starts
         const unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)p->spp / (unsigned long long)world;
         // Large renders (and jit_mode 2) wait for the build; small ones never do: their specialisation is compiled on a
@@ -384,9 +459,10 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     st.rays_shadow = ds.rays_shadow; st.miss_events = ds.misses; st.truncated = ds.truncated;
     st.shaded_vertices = ds.shaded; st.max_depth_seen = ds.max_depth_seen;
     st.term_roulette = ds.term_roulette; st.term_emitter = ds.term_emitter; st.term_light_sample = ds.term_light_sample;
-    st.dropped_contributions = ds.dropped; st.spawned_branches = ds.spawned;
+    st.dropped_contributions = ds.dropped; st.spawned_branches = ds.spawned; st.split_refusals = ds.split_refused;
     for (int k = 0; k < 64; k++) st.live_at_depth[k] = ds.live_at_depth[k];
     st.specialised = ctx->jit ? 1u : 0u;
+    st.accel_structure = (p->engine == PT_ENGINE_FP32_PHILOX && ctx->grid.n > 0) ? 1u : 0u;
     if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode == 1 && !ctx->jit)
         pt_jit_account(ctx, p->mode, p->collect_stats != 0, ms);      // small render, generic kernel: counts towards its background build
     if (p->engine == PT_ENGINE_FP64_ERAND48) {
@@ -477,6 +553,13 @@ int pt_debug_stats(pt_ctx *ctx, pt_stats *stats)
 {
     if (!ctx || !stats) return PT_ERR_ARG;
     *stats = ctx->stats;
+    return PT_OK;
+}
+
+int pt_set_acceleration(pt_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return pt_fail(ctx, PT_ERR_ARG, "acceleration mode must be 0, 1 or 2");
+    ctx->accel_mode = mode;
     return PT_OK;
 }
 
@@ -902,6 +985,9 @@ void pt_destroy(pt_ctx *ctx)
         for (int b = 0; b < 4; b++) if (ctx->q[a][b]) cudaFree(ctx->q[a][b]);
     if (ctx->d_warp_chunk) cudaFree(ctx->d_warp_chunk);
     if (ctx->d_spawn) cudaFree(ctx->d_spawn);
+    if (ctx->d_grid_start) cudaFree(ctx->d_grid_start);
+    if (ctx->d_grid_items) cudaFree(ctx->d_grid_items);
+    if (ctx->d_grid_sph) cudaFree(ctx->d_grid_sph);
     if (ctx->d_counts) cudaFree(ctx->d_counts);
     if (ctx->d_launch_rec) cudaFree(ctx->d_launch_rec);
     if (ctx->d_stamps) cudaFree(ctx->d_stamps);

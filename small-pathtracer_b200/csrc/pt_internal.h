@@ -52,6 +52,14 @@ struct pt_ctx {
     MatF32 *d_mats = nullptr;          // indexed by code
     float4 *d_sphf = nullptr;          // SceneF32::sphf mirrored in global memory (staged into shared memory by k_bounce)
     int n_codes_alloc = 0;
+    // acceleration structure (pt_set_acceleration): uniform grid over the small spheres
+    int accel_mode = 1;
+    GridDev grid{};                    // device pointers + geometry (grid.n == 0: brute force)
+    std::vector<unsigned int> h_grid_start, h_grid_items;
+    std::vector<float4> h_grid_sph;
+    unsigned int *d_grid_start = nullptr, *d_grid_items = nullptr;
+    float4 *d_grid_sph = nullptr;
+    size_t grid_start_cap = 0, grid_items_cap = 0, grid_sph_cap = 0;
     bool fp32_ok = false;              // scene fits the FP32 constant layout
     std::string fp32_why;
     // render state

@@ -63,6 +63,16 @@ struct SceneF32 {                 // lives in __constant__ memory: every access 
     float4 tilt[PT_MAX_TILT][4];  // {n.xyz, n.p0} {s.xyz, s.p0} {t.xyz, t.p0} {hs, ht, -, -}
 };
 
+// Uniform grid over the small spheres (opt-in, see pt_set_acceleration): CSR cell lists in global memory.
+struct GridDev {
+    float lo[3], cell[3], inv_cell[3];   // lower corner, cell size, 1 / cell size
+    int   res[3];                        // cells per axis
+    const unsigned int *start;           // res.x * res.y * res.z + 1 offsets into items
+    const unsigned int *items;           // sphere indices, ascending within a cell
+    const float4 *sph;                   // {centre, r^2} by sphere index (code = code_sph0 + index)
+    int   n;                             // spheres in the grid (0 = no grid)
+};
+
 struct MatF32 {                   // global memory, indexed by CODE (divergent index, so NOT constant memory)
     float4 c_refl;                // c.xyz, refl (int bits)
     float4 e_type;                // e.xyz, type (int bits)
@@ -74,7 +84,7 @@ struct DevStats {                 // device-side counters (unsigned long long fo
     unsigned long long paths, rays_camera, rays_scatter, rays_shadow, shaded, misses, truncated;
     unsigned int max_depth_seen, pad;
     // collect_stats only
-    unsigned long long term_roulette, term_emitter, term_light_sample, dropped, spawned;
+    unsigned long long term_roulette, term_emitter, term_light_sample, dropped, spawned, split_refused;
     unsigned long long live_at_depth[64];
 };
 

@@ -104,9 +104,11 @@ template <int MODE> void launch_bounce(bool stats, bool glossy, int blocks, cuda
         cudaLaunchKernel((const void *)jk->kern, dim3(blocks), dim3(PT_BLOCK), args, 0, s);
         return;
     }
-    // ahead-of-time build: DIFF-only scenes (every scene of the reference) run the instantiation without SPEC / REFR code
-    if (stats) { if (glossy) k_bounce<MODE, true, true><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, true, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
-    else { if (glossy) k_bounce<MODE, false, true><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, false, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
+    // ahead-of-time build: DIFF-only scenes (every scene of the reference) run the instantiation without SPEC / REFR code;
+    // scenes whose small spheres sit in the uniform grid run the GRID instantiation (built with every material)
+    if (P.grid.n > 0) { if (stats) k_bounce<MODE, true, true, true><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, false, true, true><<<blocks, PT_BLOCK, 0, s>>>(P); }
+    else if (stats) { if (glossy) k_bounce<MODE, true, true, false><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, true, false, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
+    else { if (glossy) k_bounce<MODE, false, true, false><<<blocks, PT_BLOCK, 0, s>>>(P); else k_bounce<MODE, false, false, false><<<blocks, PT_BLOCK, 0, s>>>(P); }
 }
 
 }  // namespace
@@ -248,11 +250,12 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
         P.use_magic = (owned_pixels < (1ull << 24) && w < 65536 && tile < 65536) ? 1 : 0;
+        P.grid = ctx->grid;
         P.key_low = PT_KEY_CODE_BITS;
         P.rect_tmin = p->robust_eps ? PT_EPS_F : 1.401298464e-45f;      // reference: no epsilon on rectangles (:106)
         P.wrap_once = owned_pixels >= 32ull ? 1 : 0;
         P.max_depth = p->max_depth > 0 ? p->max_depth : 4096;
-        if (P.max_depth > 65000) P.max_depth = 65000;
+        if (P.max_depth > 8000) P.max_depth = 8000;      // depth has 13 bits in a path record
         const pt_camera &c = ctx->cam;
         P.cam_o[0] = (float)c.origin.x; P.cam_o[1] = (float)c.origin.y; P.cam_o[2] = (float)c.origin.z;
         P.cam_base[0] = (float)(c.lower_left_corner.x - c.origin.x);
@@ -361,7 +364,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int *d_id, cudaStream_t s)
 {
     if (!ctx->fp32_ok) return pt_fail(ctx, PT_ERR_ARG, "scene does not fit the FP32 engine: " + ctx->fp32_why);
-    if (ctx->jit_mode >= 2) {       // specialisation forced: answer with the closest_hit of the scene-specialised build
+    if (ctx->jit_mode >= 2 && ctx->grid.n == 0) {       // specialisation forced: answer with the closest_hit of the scene-specialised build
         const PtJitKernel *jk = pt_jit_get(ctx, PT_MODE_COS, false, true);
         void *dptr = nullptr;
         size_t bytes = 0;
@@ -378,7 +381,8 @@ int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int
     }
     ctx->stats.specialised = 0;
     PT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_scene, ctx->h_scene32, sizeof(SceneF32), 0, cudaMemcpyHostToDevice, s));
-    k_intersect_fp32<<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats, ctx->d_sphf);
+    if (ctx->grid.n > 0) k_intersect_fp32<true><<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats, ctx->d_sphf, ctx->grid);
+    else k_intersect_fp32<false><<<(n + 127) / 128, 128, 0, s>>>(d_rays, n, d_t, d_id, ctx->d_mats, ctx->d_sphf, ctx->grid);
     PT_CUDA(ctx, cudaGetLastError());
     return PT_OK;
 }

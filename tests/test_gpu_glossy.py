@@ -53,7 +53,7 @@ def test_gate2_three_sigma_on_mirror_and_glass():
         # production: both arms while depth <= 2; its per-sample variance is the oracle's (same estimator)
         c.render(ptb.params(w, h, spp, mode=1, seed=78))
         m2, st2 = c.readback()
-        assert st2.spawned_branches > 0 and st2.truncated == 0
+        assert st2.spawned_branches > 0 and st2.truncated == 0 and st2.split_refusals == 0
     for name, m, var in (("one arm", m1, var1), ("split", m2, var_o)):
         z, se = _z(m, var / spp, omean, var_o / n_o)
         informative = se > 1e-9

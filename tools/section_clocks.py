@@ -8,7 +8,7 @@ os.environ["PTB200_CACHE_DIR"] = "off"
 from _pkg import ptb
 scene = sys.argv[1] if len(sys.argv) > 1 else "A"
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-names = ["pop + regeneration", "Philox + camera ray", "closest hit", "material fetch + refine + normal", "roulette + sampling (+ shadow ray)", "-", "-", "accumulate + loop back"]
+names = ["pop + regeneration", "Philox + camera ray", "closest hit", "material fetch + refine + normal", "roulette + sampling (+ shadow ray)", "accumulation + reconvergence", "-", "push + loop back"]
 for w, h, spp in ((4, 1, 512), (512, 512, 32)):
     with ptb.Context(ptb.builtin_scene(scene, w, h)) as c:
         c.set_specialisation(2)
