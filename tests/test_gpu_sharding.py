@@ -92,6 +92,48 @@ def test_two_processes_assemble_through_cuda_ipc(tmp_path):
             assert np.array_equal(np.load(out + str(rep) + ".npy") / spp, c.readback()[0])
 
 
+def _host_worker(rank, world, port, w, h, spp, tile, out_path):
+    import os, sys
+    import torch
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from _pkg import ptb as P
+    from small_pathtracer_b200 import dist as pdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = P.builtin_scene("A", w, h)
+    with P.Context(sc, device=0) as c:
+        host = pdist.HostImage(c, h, w, rank, world, dst=0)
+        for rep in range(2):
+            c.render(P.params(w, h, spp, mode=0, seed=30 + rep, tile_rows=tile, rank=rank, world=world))
+            c.readback_owned(host.array)              # this rank's rows, DMA'd into the image every rank maps
+            dist.barrier()
+            if rank == 0:
+                np.save(out_path + str(rep) + ".npy", np.array(host.array))
+            dist.barrier()
+        host.close()
+    dist.destroy_process_group()
+
+
+def test_two_processes_assemble_in_shared_host_memory(tmp_path):
+    # the end-to-end path of a multi-GPU render: every rank copies its own row tiles device -> host into ONE image in POSIX
+    # shared memory (pt_readback_owned); nothing funnels through rank 0's GPU.  7-row tiles over 45 rows: ragged last tile.
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    w, h, spp, tile = 64, 45, 8, 7
+    out = str(tmp_path / "host")
+    mp.spawn(_host_worker, args=(2, port, w, h, spp, tile, out), nprocs=2, join=True)
+    sc = ptb.builtin_scene("A", w, h)
+    with ptb.Context(sc) as c:
+        for rep in range(2):
+            c.render(ptb.params(w, h, spp, mode=0, seed=30 + rep))
+            assert np.array_equal(np.load(out + str(rep) + ".npy"), c.readback()[0])
+
+
 def test_single_process_multi_gpu_render():
     # pt_render_multi: one context per device, resolve kernels store into device 0's image over peer memory
     import torch
