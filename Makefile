@@ -18,8 +18,9 @@ $(OBJDIR):
 $(OBJDIR)/pt_validate.o: $(CSRC)/pt_validate.cu $(CSRC)/pt_scene_dev.h $(CSRC)/pt_internal.h include/ptb200.h include/ptb200_detmath.h | $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@ 2> $(OBJDIR)/pt_validate.ptxas.log || (cat $(OBJDIR)/pt_validate.ptxas.log; false)
 
+# FP32 production engine: no implicit FMA contraction either (every FMA is an explicit fmaf), so that this build and the NVRTC one agree bit for bit
 $(OBJDIR)/pt_wavefront.o: $(CSRC)/pt_wavefront.cu $(CSRC)/pt_kernel.cuh $(CSRC)/pt_scene_dev.h $(CSRC)/pt_internal.h $(CSRC)/pt_rng.cuh include/ptb200.h | $(OBJDIR)
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/pt_wavefront.ptxas.log || (cat $(OBJDIR)/pt_wavefront.ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@ 2> $(OBJDIR)/pt_wavefront.ptxas.log || (cat $(OBJDIR)/pt_wavefront.ptxas.log; false)
 
 $(OBJDIR)/pt_kernel_src.h: $(CSRC)/pt_scene_dev.h $(CSRC)/pt_rng.cuh $(CSRC)/pt_kernel.cuh tools/embed_kernel_src.py | $(OBJDIR)
 	python3 tools/embed_kernel_src.py $@ $(CSRC)/pt_scene_dev.h $(CSRC)/pt_rng.cuh $(CSRC)/pt_kernel.cuh

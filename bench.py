@@ -51,17 +51,21 @@ def read_peaks():
 
 
 def traffic_per_launch(workload, launches_per_step):
-    """DRAM bytes per k_bounce launch — a PROFILE CONSTANT, not measured in this run: whole-step dram__bytes_read +
-    dram__bytes_write of the committed ncu --set full capture of this workload (profiles/r02_traffic.json, falling back
-    to round 1's file) divided by the launches of a step, like `avg_launch_ms`.  None when no capture exists."""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
-        try:
-            with open(os.path.join(ROOT, "profiles", name)) as f:
-                t = json.load(f)[workload]
-            return t["dram_bytes_per_step"] / max(1, launches_per_step), f"profiles/{name} (ncu --set full capture, constant)"
-        except Exception:               # noqa: BLE001
-            continue
-    return None, None
+    """DRAM bytes per k_bounce launch — a PROFILE CONSTANT, not measured in this run: dram__bytes_read + dram__bytes_write of
+    the committed ncu --set full capture of a main launch of this workload (profiles/r02_traffic.json; round 1's file held
+    whole-step figures).  None when no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_per_launch"], "profiles/r02_traffic.json (ncu --set full capture of a main launch; a constant, not measured in this run)"
+    except Exception:                   # noqa: BLE001
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_per_step"] / max(1, launches_per_step), "profiles/r01_traffic.json (round-1 capture, whole step / launches; a constant)"
+    except Exception:                   # noqa: BLE001
+        return None, None
 
 
 class ClockSampler:
@@ -391,7 +395,7 @@ def main():
     _, img_e2e = e2e_step()
     e2e_check = None
     if rank == 0 and world > 1 and full is not None:                        # the host-assembled picture is the device-assembled one
-        e2e_check = bool(np.array_equal(np.asarray(img_e2e), (full / float(spp)).cpu().numpy()))
+        e2e_check = bool(np.array_equal(np.asarray(img_e2e), full.cpu().numpy() * (1.0 / float(spp))))      # (the library scales by the reciprocal too)
     barrier()
     e2e_times = []
     for _ in range(max(1, min(args.steps, 10))):

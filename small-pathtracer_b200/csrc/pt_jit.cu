@@ -163,6 +163,10 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     // Cone sampling of many sphere lights keeps a shadow-ray loop's state live across the unrolled scan: inlined, the
     // 64-register budget spills ~1.7 KB per thread (synthetic scene: 23 Mpaths/s); as a call, 53 Mpaths/s.
     if (mode == PT_MODE_NEE_CONE_SPHERE && S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX && S.n_lights > 1) h += "#define PT_NOINLINE_HIT 1\n";
+    // Long immediate sphere tables make the kernel instruction-fetch bound (C4: `no_instruction` is the top stall, 4.4 per issue): the
+    // warps of a block then iterate in lockstep (one block-wide barrier per bounce) and walk the straight-line scan together,
+    // sharing instruction-cache lines: +9.5 % on C4 (-3 % on scene A, where it stays off).
+    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) h += "#ifndef PT_NO_LOCKSTEP\n#define PT_LOCKSTEP 1\n#endif\n";
     if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates
         std::snprintf(b, sizeof b, "#define PT_J_SPH_IMM %d\nconstexpr float PT_J_SPHF[%d][4] = {\n", PT_JIT_SPH_IMM_MAX, S.n_sph4);
         h += b;
@@ -228,7 +232,9 @@ int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::strin
             else cur += *q;
         }
     }
-    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    // --fmad=false: the compiler never contracts a * b + c on its own, every FMA of the kernel is an explicit fmaf; that is what keeps this
+    // build and the ahead-of-time one (nvcc -fmad=false) bit-identical whatever the surrounding code looks like
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", "--fmad=false"};
     for (const std::string &x : extra) opts.push_back(x.c_str());
     const nvrtcResult rc = n.CompileProgram(prog, (int)opts.size(), opts.data());
     size_t ls = 0;

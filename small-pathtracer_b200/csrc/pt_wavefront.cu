@@ -101,7 +101,9 @@ template <int MODE> void launch_bounce(bool stats, bool glossy, int blocks, cuda
 {
     if (jk) {           // scene-specialised module (pt_jit.cu): same KParams, launched through its kernel handle
         void *args[] = {(void *)&P};
-        cudaLaunchKernel((const void *)jk->kern, dim3(blocks), dim3(PT_BLOCK), args, 0, s);
+        // (PTB200_JIT_BLOCK: tuning aid, the block size a module built with -DPT_BLOCK=... through PTB200_JIT_OPTS expects)
+        static const int jit_block = std::getenv("PTB200_JIT_BLOCK") ? std::max(32, std::atoi(std::getenv("PTB200_JIT_BLOCK"))) : PT_BLOCK;
+        cudaLaunchKernel((const void *)jk->kern, dim3(blocks * PT_BLOCK / jit_block), dim3(jit_block), args, 0, s);
         return;
     }
     // ahead-of-time build: DIFF-only scenes (every scene of the reference) run the instantiation without SPEC / REFR code;
@@ -171,17 +173,25 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 
     int it_total = 0;
     if (owned_pixels > 0 && p->spp > 0) {
-        const unsigned long long total = owned_pixels * (unsigned long long)p->spp;
+        // pixel blocks (KParams::blk_pixels): every sample of a block before the next block, accumulators of a block L2-resident
+        unsigned long long blk_target = 1ull << 19;                      // 512 Ki pixels = 12.6 MB of fixed-point accumulators
+        if (const char *e = std::getenv("PTB200_BLOCK_PIXELS")) blk_target = std::max(1ll, std::atoll(e));
+        unsigned long long n_blk = (owned_pixels + blk_target - 1) / blk_target;
+        if (n_blk > (unsigned long long)owned_rows) n_blk = (unsigned long long)owned_rows;
+        if (n_blk * (unsigned long long)p->spp >= (1ull << 31)) n_blk = 1;             // (block * spp + sample is a 32-bit value)
+        const unsigned long long blk_rows = ((unsigned long long)owned_rows + n_blk - 1) / n_blk;
+        const unsigned long long blk_pixels = blk_rows * (unsigned long long)w;
+        const unsigned long long total = n_blk * blk_pixels * (unsigned long long)p->spp;     // incl. the (< n_blk) skipped rows
         // queue capacity = path slots in flight = threads per launch.  Default: PT_DEFAULT_WAVES full waves of resident
         // blocks (no launch ends with a partially filled wave); the queues are touched once per launch, not per bounce.
         int cap = p->queue_capacity;
         const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
         if (cap <= 0) cap = (int)(PT_DEFAULT_WAVES * wave);
         {   // never more slots than paths (rounded up to whole blocks)
-            const unsigned long long need = (total + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
+            const unsigned long long need = (total + 1023) / 1024 * 1024;
             if ((unsigned long long)cap > need) cap = (int)need;
         }
-        cap = (cap + PT_BLOCK - 1) / PT_BLOCK * PT_BLOCK;
+        cap = (cap + 1023) / 1024 * 1024;              // whole blocks for any block size up to 1024
         int rc = ensure_queues(ctx, cap, stats);
         if (rc) return rc;
 
@@ -245,7 +255,8 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         }
         P.total_paths = total;
         P.owned_pixels = (unsigned int)owned_pixels;
-        P.inv_owned_pixels = 1.0 / (double)owned_pixels;
+        P.blk_pixels = (unsigned int)blk_pixels; P.blk_rows = (unsigned int)blk_rows; P.n_blk = (unsigned int)n_blk; P.owned_rows = (unsigned int)owned_rows;
+        P.inv_blk_pixels = 1.0 / (double)blk_pixels;
         P.w = w; P.h = h; P.spp = p->spp; P.tile_rows = tile; P.rank = p->rank; P.world = world;
         P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
@@ -253,7 +264,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.grid = ctx->grid;
         P.key_low = PT_KEY_CODE_BITS;
         P.rect_tmin = p->robust_eps ? PT_EPS_F : 1.401298464e-45f;      // reference: no epsilon on rectangles (:106)
-        P.wrap_once = owned_pixels >= 32ull ? 1 : 0;
+        P.wrap_once = blk_pixels >= 32ull ? 1 : 0;
         P.max_depth = p->max_depth > 0 ? p->max_depth : 4096;
         if (P.max_depth > 8000) P.max_depth = 8000;      // depth has 13 bits in a path record
         const pt_camera &c = ctx->cam;

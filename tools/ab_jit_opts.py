@@ -19,6 +19,10 @@ else:
     wl = sys.argv[1]
     for opts in sys.argv[2:]:
         env = dict(os.environ, PTB200_JIT_OPTS="" if opts in ("-", "generic") else opts, PTB200_CACHE_DIR="off", AB_SPEC="0" if opts == "generic" else "2")
+        env.pop("PTB200_JIT_BLOCK", None)
+        for tok in opts.split():
+            if tok.startswith("-DPT_BLOCK="):
+                env["PTB200_JIT_BLOCK"] = tok.split("=")[1]          # the host launches the module with the block size it was built for
         for rep in range(2):
             out = subprocess.check_output([sys.executable, __file__, "child", wl], env=env, text=True).strip().splitlines()[-1]
             ms, mp, mr, spec = json.loads(out)
