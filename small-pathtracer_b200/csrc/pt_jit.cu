@@ -160,6 +160,33 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     def_f("sph_kM2", S.sph_kM2);
     def_f("light_ex", S.light_e[0]); def_f("light_ey", S.light_e[1]); def_f("light_ez", S.light_e[2]);
     def_f("light_cx", S.light_c[0]); def_f("light_cy", S.light_c[1]); def_f("light_cz", S.light_c[2]);
+    // Shadow rays toward the reference's rectangular light only ask whether the light is the closest hit: when no other slot
+    // rectangle comes near the light's (so no t can agree with the light's in all but the six code bits of a key) the other
+    // slots compete without their codes, seven issue slots each instead of eight (rect_slot<.., SH>)
+    if (mode == PT_MODE_NEE_REF_RECT && S.light_code >= 0 && S.light_code < 3 * PT_RECT_SLOTS && !std::getenv("PTB200_NO_SHADOW_RAW")) {
+        auto box = [&](int a, int k, float lo[3], float hi[3]) {        // AX 0: plane y (u = x, v = z), 1: plane z (x, y), 2: plane x (y, z)
+            const float4 r = S.slot_a[a][k];
+            const int ax = a == 0 ? 1 : a == 1 ? 2 : 0, au = a == 2 ? 1 : 0, av = a == 1 ? 1 : 2;
+            lo[ax] = hi[ax] = r.x; lo[au] = r.y; hi[au] = r.y + r.z; lo[av] = r.w; hi[av] = r.w + S.slot_b2[a][k];
+        };
+        const int la = S.light_code / PT_RECT_SLOTS, lk = S.light_code % PT_RECT_SLOTS;
+        float llo[3], lhi[3], ext = 0.f;
+        bool apart = lk < S.n_slot[la];
+        if (apart) box(la, lk, llo, lhi);
+        double dmin = 1e30;
+        for (int a = 0; a < 3 && apart; a++)
+            for (int k = 0; k < S.n_slot[a]; k++) {
+                float lo[3], hi[3];
+                box(a, k, lo, hi);
+                for (int c = 0; c < 3; c++) ext = std::max(ext, std::max(std::fabs(lo[c]), std::fabs(hi[c])));
+                if (a == la && k == lk) continue;
+                double d2 = 0;
+                for (int c = 0; c < 3; c++) { const double g = std::max(0.0, std::max((double)lo[c] - lhi[c], (double)llo[c] - hi[c])); d2 += g * g; }
+                dmin = std::min(dmin, std::sqrt(d2));
+            }
+        // two hits on one ray are at least the rectangles' distance apart; a key tie needs them within 7.6e-6 of t <= the scene's extent
+        if (apart && dmin > 1e-4 * (double)ext * 3.5) h += "#define PT_J_SHADOW_RAW 1\n";
+    }
     // Cone sampling of many sphere lights keeps a shadow-ray loop's state live across the unrolled scan: inlined, the
     // 64-register budget spills ~1.7 KB per thread (synthetic scene: 23 Mpaths/s); as a call, 53 Mpaths/s.
     if (mode == PT_MODE_NEE_CONE_SPHERE && S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX && S.n_lights > 1) h += "#define PT_NOINLINE_HIT 1\n";

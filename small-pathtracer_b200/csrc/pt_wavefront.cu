@@ -178,40 +178,55 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         if (const char *e = std::getenv("PTB200_BLOCK_PIXELS")) blk_target = std::max(1ll, std::atoll(e));
         unsigned long long n_blk = (owned_pixels + blk_target - 1) / blk_target;
         if (n_blk > (unsigned long long)owned_rows) n_blk = (unsigned long long)owned_rows;
-        if (n_blk * (unsigned long long)p->spp >= (1ull << 31)) n_blk = 1;             // (block * spp + sample is a 32-bit value)
+        if (n_blk * (unsigned long long)p->spp >= (1ull << 31)) n_blk = 1;             // (block * runs per pixel + run is a 32-bit value)
         const unsigned long long blk_rows = ((unsigned long long)owned_rows + n_blk - 1) / n_blk;
         const unsigned long long blk_pixels = blk_rows * (unsigned long long)w;
-        const unsigned long long total = n_blk * blk_pixels * (unsigned long long)p->spp;     // incl. the (< n_blk) skipped rows
         // queue capacity = path slots in flight = threads per launch.  Default: PT_DEFAULT_WAVES full waves of resident
         // blocks (no launch ends with a partially filled wave); the queues are touched once per launch, not per bounce.
         int cap = p->queue_capacity;
         const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
         if (cap <= 0) cap = (int)(PT_DEFAULT_WAVES * wave);
         {   // never more slots than paths (rounded up to whole blocks)
-            const unsigned long long need = (total + 1023) / 1024 * 1024;
+            const unsigned long long need = (n_blk * blk_pixels * (unsigned long long)p->spp + 1023) / 1024 * 1024;
             if ((unsigned long long)cap > need) cap = (int)need;
         }
         cap = (cap + 1023) / 1024 * 1024;              // whole blocks for any block size up to 1024
+        // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
+        const bool want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
+        // Sample runs (KParams::run_shift): 64 or 128 consecutive samples of a pixel per path index when a slot traces at least
+        // 64 runs in this render, else single samples.  A render of runs ends with every slot finishing a run of its own
+        // (~1-2 % of a render that size; shorter runs end so often that some lane of a warp needs the chunk step in most
+        // iterations anyway: measured, a loss below 64).  A lane that takes over spawned REFR branches has no run of its
+        // own to come back to, so those scenes keep single samples too.
+        unsigned int run_shift = 0;
+        {
+            const unsigned long long per_slot = owned_pixels * (unsigned long long)p->spp / (unsigned long long)cap;
+            unsigned long long run = std::min<unsigned long long>(128ull, per_slot / 64ull);
+            if (run < 64ull) run = 1;
+            if (const char *e = std::getenv("PTB200_RUN")) run = (unsigned long long)std::max(1ll, std::atoll(e));
+            if (want_spawn) run = 1;
+            while ((2ull << run_shift) <= run && (2ull << run_shift) <= (unsigned long long)p->spp && run_shift < 12) run_shift++;
+        }
+        const unsigned long long spp_runs = ((unsigned long long)p->spp + (1ull << run_shift) - 1) >> run_shift;
+        const unsigned long long total = n_blk * blk_pixels * spp_runs;     // path indices = runs, incl. the (< n_blk) skipped rows
         int rc = ensure_queues(ctx, cap, stats);
         if (rc) return rc;
 
         // per-iteration live counters (n[it]); counts[0] = cap (all dead => regenerate)
         const int max_it = 1 << 20;
-        if (ctx->counts_len < max_it + 4) {
+        if (ctx->counts_len < max_it + 8) {
             if (ctx->d_counts) cudaFree(ctx->d_counts);
             ctx->d_counts = nullptr; ctx->counts_len = 0;
-            PT_CUDA(ctx, cudaMalloc(&ctx->d_counts, sizeof(unsigned int) * (size_t)(max_it + 4)));
-            ctx->counts_len = max_it + 4;
+            PT_CUDA(ctx, cudaMalloc(&ctx->d_counts, sizeof(unsigned int) * (size_t)(max_it + 8)));
+            ctx->counts_len = max_it + 8;
             ctx->counts_dirty = (size_t)ctx->counts_len;
         }
-        // layout: [0..1] gen counter (u64), [2..] n[it]
         {   // clear only the prefix the previous render dirtied (+ slack for the speculative batch)
             size_t dirty = ctx->counts_dirty + 256;
             if (dirty > (size_t)ctx->counts_len) dirty = (size_t)ctx->counts_len;
+            // layout: [0..1] the generation counter (u64), [4..] n[it]
             PT_CUDA(ctx, cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned int) * dirty, s));
         }
-        // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
-        const bool want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
         if (want_spawn && ctx->spawn_warps < cap / 32) {
             if (ctx->d_spawn) cudaFree(ctx->d_spawn);
             ctx->d_spawn = nullptr; ctx->spawn_warps = 0;
@@ -239,6 +254,9 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.iters_tail = P.iters < PT_DEFAULT_ITERS_TAIL ? P.iters : PT_DEFAULT_ITERS_TAIL;
         P.iters_drain = p->bounces_per_launch > 0 ? P.iters : PT_DEFAULT_ITERS_DRAIN;
         P.drain_below = (unsigned int)wave;
+        // with sample runs the survivors of the last path indices are slots in the middle of their runs (dozens of paths each, every
+        // lane busy until its run ends): repacking them every few bounces only adds launches
+        if (run_shift > 0 && p->bounces_per_launch <= 0) P.iters_tail = PT_DEFAULT_ITERS_DRAIN;
         // tuning overrides (tools/sweep_tail.py)
         if (const char *e = std::getenv("PTB200_ITERS_TAIL")) P.iters_tail = std::atoi(e) > 0 ? std::atoi(e) : P.iters_tail;
         if (const char *e = std::getenv("PTB200_ITERS_DRAIN")) P.iters_drain = std::atoi(e) > 0 ? std::atoi(e) : P.iters_drain;
@@ -257,6 +275,8 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.owned_pixels = (unsigned int)owned_pixels;
         P.blk_pixels = (unsigned int)blk_pixels; P.blk_rows = (unsigned int)blk_rows; P.n_blk = (unsigned int)n_blk; P.owned_rows = (unsigned int)owned_rows;
         P.inv_blk_pixels = 1.0 / (double)blk_pixels;
+        P.run_shift = run_shift; P.run_mask = (1u << run_shift) - 1u; P.spp_runs = (unsigned int)spp_runs;
+        P.pix_magic = ((unsigned long long)w * h < (1ull << 24) && w < 65536) ? 1 : 0;
         P.w = w; P.h = h; P.spp = p->spp; P.tile_rows = tile; P.rank = p->rank; P.world = world;
         P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
@@ -285,7 +305,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 
         const int blocks = cap / PT_BLOCK;
         const bool glossy = (ctx->h_scene32->refl_mask & ((1 << PT_SPEC) | (1 << PT_REFR))) != 0;
-        unsigned int *n_it = ctx->d_counts + 2;
+        unsigned int *n_it = ctx->d_counts + 4;
         // Termination check without draining the pipeline: batch k+1 is enqueued before the live count
         // after batch k is read back (pinned slot + event per parity).
         unsigned int *h_n = ctx->h_pinned;                 // pinned slots + events live in the context
@@ -322,7 +342,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         }
         if (rc2 != PT_OK) { cudaStreamSynchronize(s); return rc2; }
         ctx->stats.iterations = (uint64_t)it;
-        ctx->counts_dirty = (size_t)it + 4;
+        ctx->counts_dirty = (size_t)it + 8;
         it_total = it;
     }
     if (!ctx->d_stamps) PT_CUDA(ctx, cudaMalloc(&ctx->d_stamps, 2 * sizeof(unsigned long long)));
@@ -344,7 +364,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         const int n_rec = std::min(it_total, PT_MAX_LAUNCH_RECS);
         std::vector<LaunchRec> rec(n_rec);
         unsigned long long stamps[2] = {0, 0};
-        PT_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts + 2, sizeof(unsigned int) * (size_t)(it_total + 1), cudaMemcpyDeviceToHost, s));
+        PT_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_counts + 4, sizeof(unsigned int) * (size_t)(it_total + 1), cudaMemcpyDeviceToHost, s));
         PT_CUDA(ctx, cudaMemcpyAsync(rec.data(), ctx->d_launch_rec, sizeof(LaunchRec) * (size_t)n_rec, cudaMemcpyDeviceToHost, s));
         PT_CUDA(ctx, cudaMemcpyAsync(stamps, ctx->d_stamps, sizeof stamps, cudaMemcpyDeviceToHost, s));
         PT_CUDA(ctx, cudaStreamSynchronize(s));

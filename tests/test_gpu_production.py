@@ -66,6 +66,40 @@ def test_bit_reproducible_and_queue_independent():
     assert not np.array_equal(imgs[0], other)                  # the seed matters
 
 
+@pytest.mark.parametrize("scene,mode", [("A", 0), ("A", 2), ("G", 1)])
+def test_image_does_not_depend_on_the_sample_run_length(scene, mode, monkeypatch):
+    # a path index stands for a run of 2^k consecutive samples of one pixel, traced one after the other by the lane that
+    # took it (KParams::run_shift; the library picks k from the size of the render, PTB200_RUN overrides it): every
+    # (pixel, sample) is still traced exactly once with its own Philox counters, so images and counters are bit-identical
+    # for every run length: spp no multiple of the run, a sample offset, sharded renders, launches two bounces deep (runs
+    # continue across launches through the queue).  Scene G splits paths at its glass sphere and therefore always runs
+    # single samples (also checked: same image).
+    w, h, spp = 96, 60, 44
+    sc = ptb.builtin_scene(scene, w, h)
+    out = []
+    with ptb.Context(sc) as c:
+        for run, kw in (("1", {}), ("4", {}), ("16", {"queue_capacity": 4096, "bounces_per_launch": 2}), ("64", {}), ("8", {"queue_capacity": 8192}),
+                        ("32", {"queue_capacity": 2048, "bounces_per_launch": 5})):
+            monkeypatch.setenv("PTB200_RUN", run)
+            c.render(ptb.params(w, h, spp, mode=mode, seed=5, **kw))
+            img, st = c.readback()
+            out.append((img.copy(), st.paths, st.rays, st.shaded_vertices, st.miss_events))
+        for a in out[1:]:
+            assert a[1:] == out[0][1:] and np.array_equal(a[0], out[0][0])
+        # two chunks of a progressive render (offsets 0 and 20), each with its own runs
+        monkeypatch.setenv("PTB200_RUN", "8")
+        c.render(ptb.params(w, h, 20, mode=mode, seed=5))
+        c.render(ptb.params(w, h, spp - 20, mode=mode, seed=5, sample_offset=20, accumulate=1))
+        assert np.array_equal(c.readback()[0], out[0][0])
+        # sharded, runs of 16
+        monkeypatch.setenv("PTB200_RUN", "16")
+        total = np.zeros_like(out[0][0])
+        for r in range(3):
+            c.render(ptb.params(w, h, spp, mode=mode, seed=5, tile_rows=7, rank=r, world=3, queue_capacity=2048))
+            total += c.readback()[0]
+        assert np.array_equal(total, out[0][0])
+
+
 @pytest.mark.parametrize("world,tile", [(2, 8), (8, 16), (3, 5)])
 def test_sharded_image_is_bit_identical(world, tile):
     w, h, spp = 96, 83, 32
@@ -255,7 +289,7 @@ def test_small_renders_get_their_specialisation_in_the_background(monkeypatch):
 
 
 @pytest.mark.parametrize("spec", [0, 2], ids=["generic", "specialised"])
-def test_every_pixel_gets_exactly_spp_samples(spec):
+def test_every_pixel_gets_exactly_spp_samples(spec, monkeypatch):
     # regeneration hands out (sample, pixel) pairs from per-warp chunks, with refills, wraps into the next sample, guided
     # chunk sizes near the end and row-tile arithmetic for sharded renders: the pairs must be each pixel x each sample,
     # once.  Scene: one emissive, black-bodied wall filling the view => every path returns exactly 1, so a pixel's mean
@@ -267,11 +301,15 @@ def test_every_pixel_gets_exactly_spp_samples(spec):
         sc = ptb.Scene([], [wall], [0], base.light, base.camera)
         with ptb.Context(sc) as c:
             c.set_specialisation(spec)
-            for kw in ({}, {"queue_capacity": 8192, "bounces_per_launch": 2}):
+            for kw in ({}, {"queue_capacity": 8192, "bounces_per_launch": 2}, {"run": "4"}, {"run": "32", "queue_capacity": 2048, "bounces_per_launch": 3},
+                       {"run": "8", "queue_capacity": 1024}):
+                kw = dict(kw)
+                monkeypatch.setenv("PTB200_RUN", kw.pop("run")) if "run" in kw else monkeypatch.delenv("PTB200_RUN", raising=False)
                 c.render(ptb.params(w, h, spp, mode=1, seed=4, **kw))
                 img, st = c.readback()
                 assert st.paths == w * h * spp
                 assert np.all(img == 1.0), (w, h, spp, kw, float(img.min()), float(img.max()))
+            monkeypatch.setenv("PTB200_RUN", "8")
             for world, tile in ((3, 4), (2, 1)):
                 seen = np.zeros(h, dtype=int)
                 for r in range(world):

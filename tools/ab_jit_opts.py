@@ -10,10 +10,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         c.set_specialisation(int(os.environ.get("AB_SPEC", "2")))
         best = None
         for _ in range(5):
-            c.render(ptb.params(w, h, spp, mode=mode, seed=0))
+            # (AB_CAP / AB_ITERS / AB_WORLD: queue capacity, bounces per launch, and rank 0's share of a world of that many GPUs)
+            c.render(ptb.params(w, h, spp, mode=mode, seed=0, queue_capacity=int(os.environ.get("AB_CAP", "0")), bounces_per_launch=int(os.environ.get("AB_ITERS", "0")),
+                                world=int(os.environ.get("AB_WORLD", "1")), tile_rows=8))
             st = c.stats()
             if best is None or st.render_ms < best[0]:
-                best = (st.render_ms, st.paths / st.render_ms * 1e-3, st.rays / st.render_ms * 1e-3, st.specialised)
+                best = (st.render_ms, st.paths / st.render_ms * 1e-3, st.rays / st.render_ms * 1e-3, st.specialised,
+                        f"main {st.main_kernel_ms:.3f} tail {st.tail_ms:.3f} resolve {st.resolve_ms:.3f} launches {st.iterations} ({st.tail_launches} tail)")
     print(json.dumps(best))
 else:
     wl = sys.argv[1]
@@ -25,5 +28,5 @@ else:
                 env["PTB200_JIT_BLOCK"] = tok.split("=")[1]          # the host launches the module with the block size it was built for
         for rep in range(2):
             out = subprocess.check_output([sys.executable, __file__, "child", wl], env=env, text=True).strip().splitlines()[-1]
-            ms, mp, mr, spec = json.loads(out)
-            print(f"{wl:4s} {opts:24s} {ms:9.3f} ms  {mp:9.1f} Mpaths/s  {mr:9.1f} Mrays/s  specialised={spec}", flush=True)
+            ms, mp, mr, spec, phases = json.loads(out)
+            print(f"{wl:4s} {opts:24s} {ms:9.3f} ms  {mp:9.1f} Mpaths/s  {mr:9.1f} Mrays/s  specialised={spec}  {phases}", flush=True)
