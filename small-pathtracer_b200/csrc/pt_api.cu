@@ -440,7 +440,11 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
         // Large renders (and jit_mode 2) wait for the build; small ones never do: their specialisation is compiled on a
         // host thread from the second render on and used once it is there.  Which build runs cannot be seen in the
         // image: the two perform the same operations in the same order (bit-identical, tested).
-        ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0, false, ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS);
+        // (the module is built for this render's regeneration flags too: row blocks, sample runs, one GPU or several)
+        Fp32Plan pl;
+        pt_fp32_plan(ctx, p, pl);
+        ctx->jit_flags = std::getenv("PTB200_JIT_NO_RENDER_FLAGS") ? -1 : pl.flags;
+        ctx->jit = pt_jit_get(ctx, p->mode, p->collect_stats != 0, false, ctx->jit_mode >= 2 || total >= PT_JIT_MIN_PATHS, ctx->jit_flags);
     }
     std::unique_lock<std::mutex> scene_lock(dev_mutex(ctx->device), std::defer_lock);
     if (p->engine == PT_ENGINE_FP32_PHILOX) scene_lock.lock();      // released on return, i.e. after the stream synchronised
@@ -464,7 +468,7 @@ static int render_common(pt_ctx *ctx, const pt_render_params *p, double *ext_sum
     st.specialised = ctx->jit ? 1u : 0u;
     st.accel_structure = (p->engine == PT_ENGINE_FP32_PHILOX && ctx->grid.n > 0) ? 1u : 0u;
     if (p->engine == PT_ENGINE_FP32_PHILOX && ctx->fp32_ok && ctx->jit_mode == 1 && !ctx->jit)
-        pt_jit_account(ctx, p->mode, p->collect_stats != 0, ms);      // small render, generic kernel: counts towards its background build
+        pt_jit_account(ctx, p->mode, p->collect_stats != 0, ms, ctx->jit_flags);      // small render, generic kernel: counts towards its background build
     if (p->engine == PT_ENGINE_FP64_ERAND48) {
         st.paths = ds.paths; st.rays_camera = ds.rays_camera; st.rays_scatter = ds.rays_scatter;
     } else {

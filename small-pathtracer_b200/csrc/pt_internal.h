@@ -98,6 +98,7 @@ struct pt_ctx {
     // scene specialisation: 0 = generic kernel only, 1 = specialise renders of >= PT_JIT_MIN_PATHS paths, 2 = always
     int jit_mode = 1;
     PtJitKernel *jit = nullptr;                        // kernel chosen for the render in flight (nullptr = generic)
+    int jit_flags = -1;                                // ... and the PT_RF_* flags it was asked for (-1: none)
     std::string jit_note;
     std::string err;
 };
@@ -111,10 +112,11 @@ struct PtJitKernel {
     cudaKernel_t kern_isect = nullptr;     // k_intersect_jit (pt_debug_intersect through the specialised closest_hit)
     double compile_seconds = 0;
 };
-std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false);
+// render_flags: PT_RF_* bits of the render the module is built for (regeneration branches as compile-time constants), -1 = none
+std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false, int render_flags = -1);
 int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
-PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false, bool wait = true);
-void pt_jit_account(pt_ctx *ctx, int mode, bool stats, double ms);
+PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false, bool wait = true, int render_flags = -1);
+void pt_jit_account(pt_ctx *ctx, int mode, bool stats, double ms, int render_flags = -1);
 int pt_jit_build(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds, bool *from_disk);
 #define PT_CUDA(ctx, call)                                                                      \
     do {                                                                                        \
@@ -129,6 +131,22 @@ int pt_fp64_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 int pt_fp64_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int *d_id, cudaStream_t s);
 int pt_fp64_erand48(pt_ctx *ctx, const uint16_t *d_seeds, int n_threads, int draws, double *d_out, cudaStream_t s);
 
+// How the FP32 engine lays a render out (pt_fp32_plan): row blocks, slots in flight, sample runs, and the PT_RF_* flags the
+// regeneration step of k_bounce branches on (a scene-specialised module is built for one combination of them)
+#define PT_RF_WRAP_ONCE 1      /* a block has at least 32 pixels */
+#define PT_RF_MAGIC 2          /* every index -> row division is a multiply-shift */
+#define PT_RF_WORLD1 4         /* one GPU owns every row */
+#define PT_RF_ONE_BLOCK 8      /* no row blocks */
+#define PT_RF_RUNS 16          /* sample runs */
+struct Fp32Plan {
+    long long owned_rows = 0;
+    unsigned long long owned_pixels = 0, n_blk = 1, blk_rows = 0, blk_pixels = 0, spp_runs = 0, total = 0;
+    int cap = 0;
+    unsigned int run_shift = 0;
+    bool want_spawn = false, use_magic = false, pix_magic = false;
+    int flags = 0;
+};
+void pt_fp32_plan(const pt_ctx *ctx, const pt_render_params *p, Fp32Plan &pl);
 int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double *d_sumsq, cudaStream_t s);
 int pt_fp32_intersect(pt_ctx *ctx, const double *d_rays, int n, double *d_t, int *d_id, cudaStream_t s);
 int pt_fp32_philox(pt_ctx *ctx, const uint32_t *d_ctr, const uint32_t *d_key, int n, uint32_t *d_out, cudaStream_t s, int width);

@@ -133,6 +133,60 @@ static int ensure_queues(pt_ctx *ctx, int capacity, bool stats)
     return PT_OK;
 }
 
+// The layout of a render: a pure function of the context (SM count, scene materials) and the parameters.
+void pt_fp32_plan(const pt_ctx *ctx, const pt_render_params *p, Fp32Plan &pl)
+{
+    pl = Fp32Plan();
+    const int w = p->width, h = p->height;
+    const int tile = p->tile_rows > 0 ? p->tile_rows : 8;
+    const int world = p->world > 0 ? p->world : 1;
+    const bool stats = p->collect_stats != 0;
+    // rows owned by this rank
+    const int n_tiles = (h + tile - 1) / tile;
+    for (int k = p->rank; k < n_tiles; k += world) pl.owned_rows += (k * tile + tile <= h) ? tile : (h - k * tile);
+    pl.owned_pixels = (unsigned long long)pl.owned_rows * w;
+    if (pl.owned_pixels == 0 || p->spp <= 0) return;
+    // pixel blocks (KParams::blk_pixels): every sample of a block before the next block, accumulators of a block L2-resident
+    unsigned long long blk_target = 1ull << 19;                      // 512 Ki pixels = 12.6 MB of fixed-point accumulators
+    if (const char *e = std::getenv("PTB200_BLOCK_PIXELS")) blk_target = std::max(1ll, std::atoll(e));
+    pl.n_blk = (pl.owned_pixels + blk_target - 1) / blk_target;
+    if (pl.n_blk > (unsigned long long)pl.owned_rows) pl.n_blk = (unsigned long long)pl.owned_rows;
+    if (pl.n_blk * (unsigned long long)p->spp >= (1ull << 31)) pl.n_blk = 1;             // (block * runs per pixel + run is a 32-bit value)
+    pl.blk_rows = ((unsigned long long)pl.owned_rows + pl.n_blk - 1) / pl.n_blk;
+    pl.blk_pixels = pl.blk_rows * (unsigned long long)w;
+    // queue capacity = path slots in flight = threads per launch.  Default: PT_DEFAULT_WAVES full waves of resident
+    // blocks (no launch ends with a partially filled wave); the queues are touched once per launch, not per bounce.
+    int cap = p->queue_capacity;
+    const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
+    if (cap <= 0) cap = (int)(PT_DEFAULT_WAVES * wave);
+    {   // never more slots than paths (rounded up to whole blocks)
+        const unsigned long long need = (pl.n_blk * pl.blk_pixels * (unsigned long long)p->spp + 1023) / 1024 * 1024;
+        if ((unsigned long long)cap > need) cap = (int)need;
+    }
+    pl.cap = (cap + 1023) / 1024 * 1024;              // whole blocks for any block size up to 1024
+    // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
+    pl.want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
+    // Sample runs (KParams::run_shift): 64 or 128 consecutive samples of a pixel per path index when a slot traces at least
+    // 64 runs in this render, else single samples.  A render of runs ends with every slot finishing a run of its own
+    // (~1-2 % of a render that size; shorter runs end so often that some lane of a warp needs the chunk step in most
+    // iterations anyway: measured, a loss below 64).  A lane that takes over spawned REFR branches has no run of its
+    // own to come back to, so those scenes keep single samples too.
+    {
+        const unsigned long long per_slot = pl.owned_pixels * (unsigned long long)p->spp / (unsigned long long)pl.cap;
+        unsigned long long run = std::min<unsigned long long>(128ull, per_slot / 64ull);
+        if (run < 64ull) run = 1;
+        if (const char *e = std::getenv("PTB200_RUN")) run = (unsigned long long)std::max(1ll, std::atoll(e));
+        if (pl.want_spawn) run = 1;
+        while ((2ull << pl.run_shift) <= run && (2ull << pl.run_shift) <= (unsigned long long)p->spp && pl.run_shift < 12) pl.run_shift++;
+    }
+    pl.spp_runs = ((unsigned long long)p->spp + (1ull << pl.run_shift) - 1) >> pl.run_shift;
+    pl.total = pl.n_blk * pl.blk_pixels * pl.spp_runs;     // path indices = runs, incl. the (< n_blk) skipped rows
+    pl.use_magic = pl.owned_pixels < (1ull << 24) && w < 65536 && tile < 65536;
+    pl.pix_magic = (unsigned long long)w * h < (1ull << 24) && w < 65536;
+    pl.flags = (pl.blk_pixels >= 32ull ? PT_RF_WRAP_ONCE : 0) | (pl.use_magic && pl.pix_magic ? PT_RF_MAGIC : 0) | (world == 1 ? PT_RF_WORLD1 : 0)
+             | (pl.n_blk == 1 ? PT_RF_ONE_BLOCK : 0) | (pl.run_shift > 0 ? PT_RF_RUNS : 0);
+}
+
 int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double *d_sumsq, cudaStream_t s)
 {
     if (!ctx->fp32_ok) return pt_fail(ctx, PT_ERR_ARG, "scene does not fit the FP32 engine: " + ctx->fp32_why);
@@ -143,11 +197,10 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
     if (p->mode == PT_MODE_NEE_CONE_SPHERE && ctx->h_scene32->n_lights == 0)
         return pt_fail(ctx, PT_ERR_ARG, "PT_MODE_NEE_CONE_SPHERE needs at least one emissive sphere");
 
-    // rows owned by this rank
-    long long owned_rows = 0;
-    const int n_tiles = (h + tile - 1) / tile;
-    for (int k = p->rank; k < n_tiles; k += world) owned_rows += (k * tile + tile <= h) ? tile : (h - k * tile);
-    const unsigned long long owned_pixels = (unsigned long long)owned_rows * w;
+    Fp32Plan pl;
+    pt_fp32_plan(ctx, p, pl);
+    const long long owned_rows = pl.owned_rows;
+    const unsigned long long owned_pixels = pl.owned_pixels;
     const size_t n_acc = (size_t)w * h * 3;
 
     // fixed-point accumulators
@@ -173,42 +226,11 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
 
     int it_total = 0;
     if (owned_pixels > 0 && p->spp > 0) {
-        // pixel blocks (KParams::blk_pixels): every sample of a block before the next block, accumulators of a block L2-resident
-        unsigned long long blk_target = 1ull << 19;                      // 512 Ki pixels = 12.6 MB of fixed-point accumulators
-        if (const char *e = std::getenv("PTB200_BLOCK_PIXELS")) blk_target = std::max(1ll, std::atoll(e));
-        unsigned long long n_blk = (owned_pixels + blk_target - 1) / blk_target;
-        if (n_blk > (unsigned long long)owned_rows) n_blk = (unsigned long long)owned_rows;
-        if (n_blk * (unsigned long long)p->spp >= (1ull << 31)) n_blk = 1;             // (block * runs per pixel + run is a 32-bit value)
-        const unsigned long long blk_rows = ((unsigned long long)owned_rows + n_blk - 1) / n_blk;
-        const unsigned long long blk_pixels = blk_rows * (unsigned long long)w;
-        // queue capacity = path slots in flight = threads per launch.  Default: PT_DEFAULT_WAVES full waves of resident
-        // blocks (no launch ends with a partially filled wave); the queues are touched once per launch, not per bounce.
-        int cap = p->queue_capacity;
+        const unsigned long long n_blk = pl.n_blk, blk_rows = pl.blk_rows, blk_pixels = pl.blk_pixels, spp_runs = pl.spp_runs, total = pl.total;
+        const int cap = pl.cap;
         const long long wave = (long long)ctx->sm_count * PT_BLOCKS_PER_SM * PT_BLOCK;
-        if (cap <= 0) cap = (int)(PT_DEFAULT_WAVES * wave);
-        {   // never more slots than paths (rounded up to whole blocks)
-            const unsigned long long need = (n_blk * blk_pixels * (unsigned long long)p->spp + 1023) / 1024 * 1024;
-            if ((unsigned long long)cap > need) cap = (int)need;
-        }
-        cap = (cap + 1023) / 1024 * 1024;              // whole blocks for any block size up to 1024
-        // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
-        const bool want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
-        // Sample runs (KParams::run_shift): 64 or 128 consecutive samples of a pixel per path index when a slot traces at least
-        // 64 runs in this render, else single samples.  A render of runs ends with every slot finishing a run of its own
-        // (~1-2 % of a render that size; shorter runs end so often that some lane of a warp needs the chunk step in most
-        // iterations anyway: measured, a loss below 64).  A lane that takes over spawned REFR branches has no run of its
-        // own to come back to, so those scenes keep single samples too.
-        unsigned int run_shift = 0;
-        {
-            const unsigned long long per_slot = owned_pixels * (unsigned long long)p->spp / (unsigned long long)cap;
-            unsigned long long run = std::min<unsigned long long>(128ull, per_slot / 64ull);
-            if (run < 64ull) run = 1;
-            if (const char *e = std::getenv("PTB200_RUN")) run = (unsigned long long)std::max(1ll, std::atoll(e));
-            if (want_spawn) run = 1;
-            while ((2ull << run_shift) <= run && (2ull << run_shift) <= (unsigned long long)p->spp && run_shift < 12) run_shift++;
-        }
-        const unsigned long long spp_runs = ((unsigned long long)p->spp + (1ull << run_shift) - 1) >> run_shift;
-        const unsigned long long total = n_blk * blk_pixels * spp_runs;     // path indices = runs, incl. the (< n_blk) skipped rows
+        const bool want_spawn = pl.want_spawn;
+        const unsigned int run_shift = pl.run_shift;
         int rc = ensure_queues(ctx, cap, stats);
         if (rc) return rc;
 
@@ -276,11 +298,11 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.blk_pixels = (unsigned int)blk_pixels; P.blk_rows = (unsigned int)blk_rows; P.n_blk = (unsigned int)n_blk; P.owned_rows = (unsigned int)owned_rows;
         P.inv_blk_pixels = 1.0 / (double)blk_pixels;
         P.run_shift = run_shift; P.run_mask = (1u << run_shift) - 1u; P.spp_runs = (unsigned int)spp_runs;
-        P.pix_magic = ((unsigned long long)w * h < (1ull << 24) && w < 65536) ? 1 : 0;
+        P.pix_magic = pl.pix_magic ? 1 : 0;
         P.w = w; P.h = h; P.spp = p->spp; P.tile_rows = tile; P.rank = p->rank; P.world = world;
         P.magic_w = ((1ull << 40) + (unsigned long long)w - 1) / (unsigned long long)w;
         P.magic_tile = ((1ull << 40) + (unsigned long long)tile - 1) / (unsigned long long)tile;
-        P.use_magic = (owned_pixels < (1ull << 24) && w < 65536 && tile < 65536) ? 1 : 0;
+        P.use_magic = pl.use_magic ? 1 : 0;
         P.grid = ctx->grid;
         P.key_low = PT_KEY_CODE_BITS;
         P.rect_tmin = p->robust_eps ? PT_EPS_F : 1.401298464e-45f;      // reference: no epsilon on rectangles (:106)
