@@ -16,7 +16,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             st = c.stats()
             if best is None or st.render_ms < best[0]:
                 best = (st.render_ms, st.paths / st.render_ms * 1e-3, st.rays / st.render_ms * 1e-3, st.specialised,
-                        f"main {st.main_kernel_ms:.3f} tail {st.tail_ms:.3f} resolve {st.resolve_ms:.3f} launches {st.iterations} ({st.tail_launches} tail)")
+                        f"main {st.main_kernel_ms:.3f} tail {st.tail_ms:.3f} resolve {st.resolve_ms:.3f} launches {st.iterations} ({st.tail_launches} tail) misses/path {st.miss_events / st.paths:.5f}")
     print(json.dumps(best))
 else:
     wl = sys.argv[1]
