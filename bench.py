@@ -260,6 +260,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     # 10-row tiles: 2160 rows = 216 tiles, the same number of tiles (and rows) for every rank at 2, 4 and 8 GPUs
     tile_rows = 10 if world > 1 else 8
+    if os.environ.get("BENCH_TILE_ROWS"):                    # tuning aid
+        tile_rows = int(os.environ["BENCH_TILE_ROWS"])
     scene = ptb.builtin_scene(scene_name, w, h)
     ctx = ptb.Context(scene, device=local_rank)
     params = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=rank, world=world)
@@ -352,6 +354,11 @@ def main():
     else:
         paths, rays, shaded, launches_all, kernel_ms_all = my_paths, my_rays, my_shaded, float(launches), kernel_ms
     phases = {k: {"max_over_ranks_ms": float(ph_t[i]), "min_over_ranks_ms": float(ph_min[i])} for i, k in enumerate(ph_keys)}
+    if world > 1:                       # this rank's own render, rank by rank (which GPUs are the slow ones)
+        own = torch.zeros(world, dtype=torch.float64, device=device)
+        own[rank] = ph["own_render"] / args.steps
+        dist.all_reduce(own, op=dist.ReduceOp.SUM)
+        phases["own_render_by_rank_ms"] = [round(float(x), 3) for x in own]
     phases["note"] = ("per step; generating / tail / resolve from %globaltimer stamps the kernels take themselves (pt_stats), own_render = CUDA events "
                       "around this rank's pt_render_into, wait_and_barrier = the rest of the step (waiting for the slowest rank + the barrier / gather)")
     value = paths / total_ms * 1e-3

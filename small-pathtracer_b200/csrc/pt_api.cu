@@ -871,7 +871,7 @@ int pt_host_unregister(pt_ctx *ctx, void *host_ptr)
 }
 
 // The rows this rank owns (row tiles k % world == rank of the last render), as means, into the caller's FULL-SIZE
-// host image: one DMA per row tile, each rank over its own PCIe link.  With the image in memory every rank maps
+// host image: one strided DMA for the rank's full tiles, each rank over its own PCIe link.  With the image in memory every rank maps
 // (POSIX shared memory, registered through pt_host_register) the host-side image assembles without a gather.
 int pt_readback_owned(pt_ctx *ctx, double *host_image, pt_stats *stats)
 {
@@ -895,9 +895,21 @@ int pt_readback_owned(pt_ctx *ctx, double *host_image, pt_stats *stats)
     const int world = p.world > 0 ? p.world : 1, tile = p.tile_rows > 0 ? p.tile_rows : 8;
     const int n_tiles = (p.height + tile - 1) / tile;
     const size_t row = (size_t)p.width * 3;
-    for (int k = p.rank; k < n_tiles; k += world) {
-        const int y0 = k * tile, rows = std::min(tile, p.height - y0);
-        PT_CUDA(ctx, cudaMemcpyAsync(host_image + (size_t)y0 * row, ctx->d_mean + (size_t)y0 * row, (size_t)rows * row * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // the full tiles lie a constant world * tile rows apart: ONE strided DMA (a tile = one "row" of the 2D copy), then the
+    // ragged last tile of the image if it is this rank's
+    int n_full = 0, k_last = -1;
+    for (int k = p.rank; k < n_tiles; k += world) { if (k * tile + tile <= p.height) n_full++; else k_last = k; }
+    const size_t pitch = (size_t)world * tile * row * sizeof(double), width = (size_t)tile * row * sizeof(double), y_first = (size_t)p.rank * tile;
+    size_t max_pitch = 0;
+    { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMaxPitch, ctx->device); max_pitch = (size_t)v; }
+    if (n_full > 0 && pitch <= max_pitch)
+        PT_CUDA(ctx, cudaMemcpy2DAsync(host_image + y_first * row, pitch, ctx->d_mean + y_first * row, pitch, width, (size_t)n_full, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+        for (int k = p.rank, i = 0; i < n_full; k += world, i++)
+            PT_CUDA(ctx, cudaMemcpyAsync(host_image + (size_t)k * tile * row, ctx->d_mean + (size_t)k * tile * row, width, cudaMemcpyDeviceToHost, ctx->stream));
+    if (k_last >= 0) {
+        const size_t y0 = (size_t)k_last * tile;
+        PT_CUDA(ctx, cudaMemcpyAsync(host_image + y0 * row, ctx->d_mean + y0 * row, ((size_t)p.height - y0) * row * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     PT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (stats) *stats = ctx->stats;
