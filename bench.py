@@ -369,6 +369,7 @@ def main():
     # N > 1: every rank renders its tiles and DMAs ITS rows into ONE host image in shared memory (pt_readback_owned),
     #        each over its own PCIe link; rank 0's host then holds the whole FP64 picture.
     host_img = None
+    params_own = ptb.params(w, h, spp, mode=mode, engine=ptb.PT_ENGINE_FP32_PHILOX, seed=0, tile_rows=tile_rows, rank=rank, world=world, owned_rows_only=1)
     if world > 1:
         try:
             host_img = pdist.HostImage(ctx, h, w, rank, world, dst=0)
@@ -380,7 +381,7 @@ def main():
         t0 = time.perf_counter()
         ctx.update_scene(scene)                                             # H2D: scene table + camera (pt_scene_upload, in place)
         if world > 1 and host_img is not None:
-            ctx.render(params)                                              # this rank's tiles into its own accumulators
+            ctx.render(params_own)                                          # this rank's tiles into its own accumulators (only its rows are resolved)
             ctx.readback_owned(host_img.array)                              # D2H: its rows into the shared host image
             dist.barrier()
             host = host_img.array if rank == 0 else None

@@ -662,6 +662,18 @@ __global__ void k_scale(const double *__restrict__ in, double *__restrict__ out,
     if (i < n) out[i] = in[i] * scale;
 }
 
+// the same for the rows of one rank only (row tiles k % world == rank): pt_readback_owned moves nothing else
+__global__ void k_scale_owned(const double *__restrict__ in, double *__restrict__ out, unsigned long long owned_elems, int row_elems, int tile_rows, int rank, int world, double scale)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= owned_elems) return;
+    const unsigned int row_local = (unsigned int)(i / (unsigned int)row_elems), e = (unsigned int)(i - (unsigned long long)row_local * (unsigned int)row_elems);
+    const unsigned int tile = row_local / (unsigned int)tile_rows;
+    const unsigned int y = (tile * (unsigned int)world + (unsigned int)rank) * (unsigned int)tile_rows + (row_local - tile * (unsigned int)tile_rows);
+    const size_t idx = (size_t)y * (size_t)row_elems + e;
+    out[idx] = in[idx] * scale;
+}
+
 // device -> caller's (pageable) buffer.  Each LANE owns a stream and two pinned staging blocks: the copy of block k+1
 // over PCIe overlaps the host memcpy of block k.  One lane's memcpy (~10 GB/s) is slower than PCIe, so images of 4 MB
 // and more are split over PT_STAGE_LANES lanes, each driven by its own host thread.
@@ -890,11 +902,17 @@ int pt_readback_owned(pt_ctx *ctx, double *host_image, pt_stats *stats)
     }
     const double *src = ctx->d_sum_ext ? ctx->d_sum_ext : ctx->d_sum;
     const double spp = (double)(ctx->accum_spp > 0 ? ctx->accum_spp : p.spp);
-    k_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, n, spp > 0 ? 1.0 / spp : 1.0);
-    PT_CUDA(ctx, cudaGetLastError());
     const int world = p.world > 0 ? p.world : 1, tile = p.tile_rows > 0 ? p.tile_rows : 8;
     const int n_tiles = (p.height + tile - 1) / tile;
     const size_t row = (size_t)p.width * 3;
+    {   // sums -> means, this rank's rows only
+        unsigned long long owned_rows = 0;
+        for (int k = p.rank; k < n_tiles; k += world) owned_rows += (unsigned long long)std::min(tile, p.height - k * tile);
+        const unsigned long long owned_elems = owned_rows * row;
+        if (owned_elems > 0)
+            k_scale_owned<<<(unsigned)((owned_elems + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->d_mean, owned_elems, (int)row, tile, p.rank, world, spp > 0 ? 1.0 / spp : 1.0);
+        PT_CUDA(ctx, cudaGetLastError());
+    }
     // the full tiles lie a constant world * tile rows apart: ONE strided DMA (a tile = one "row" of the 2D copy), then the
     // ragged last tile of the image if it is this rank's
     int n_full = 0, k_last = -1;
