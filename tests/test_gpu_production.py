@@ -420,6 +420,35 @@ def test_fp32_engine_edge_cases():
         assert c.stats().accel_structure == 1
 
 
+@pytest.mark.parametrize("spec", [0, 2], ids=["generic", "specialised"])
+def test_images_beyond_2_pow_24_pixels_get_every_sample_once(spec, monkeypatch):
+    # maximum sizes: more than 2^24 pixels (the multiply-shift index divisions are exact below that; beyond it the kernel
+    # divides), many row blocks whose last one is short by a few rows, a very wide and a very tall image, row tiles of an odd
+    # height over 3 ranks, with and without sample runs.  Emissive black-bodied wall => a pixel's mean is exactly 1.0 if and
+    # only if it received exactly spp samples (see test_every_pixel_gets_exactly_spp_samples).
+    from small_pathtracer_b200 import dist as pdist
+    for w, h, spp, run in ((5000, 3403, 2, "1"), (5000, 3403, 3, "2"), (65535, 257, 1, "1"), (3, 65535, 5, "4")):
+        base = ptb.builtin_scene("A", w, h)
+        wall = ptb.rect(ptb.PT_PLANE_XY, -1e4, 1e4, -1e4, 1e4, 0.0, e=(1, 1, 1), c=(0, 0, 0))
+        sc = ptb.Scene([], [wall], [0], base.light, base.camera)
+        monkeypatch.setenv("PTB200_RUN", run)
+        with ptb.Context(sc) as c:
+            c.set_specialisation(spec)
+            c.render(ptb.params(w, h, spp, mode=1, seed=9))
+            view, st = c.readback_view()
+            assert st.paths == w * h * spp
+            assert float(view.min()) == 1.0 and float(view.max()) == 1.0, (w, h, spp, float(view.min()), float(view.max()))
+            seen = np.zeros(h, dtype=int)
+            for r in range(3):
+                c.render(ptb.params(w, h, spp, mode=1, seed=9, tile_rows=7, rank=r, world=3))
+                view, st = c.readback_view()
+                rows = np.asarray(pdist.owned_rows(h, 7, r, 3), dtype=int)
+                assert st.paths == len(rows) * w * spp
+                assert np.all(view[rows] == 1.0) and float(view.sum()) == float(len(rows)) * w * 3
+                seen[rows] += 1
+            assert np.all(seen == 1)
+
+
 def test_overflow_rectangles_generic_and_specialised():
     # 17 + 24 rectangles, 29 of them in the XZ class (16 unrolled slots + 13 in the overflow loop)
     w, h = 96, 72
