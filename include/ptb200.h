@@ -278,7 +278,8 @@ int pt_debug_ffma_peak(pt_ctx *ctx, double *tflops, double *sm_clock_mhz);
 /* Scene specialisation of the FP32 engine.  The reference's scene is a source literal (src/smallpt.cpp:287-311), so
  * its compiler folds every plane constant; pt_render does the same for an uploaded scene by compiling, with NVRTC,
  * a build of the bounce kernel in which the scene's rectangle constants and primitive counts are immediates (cached
- * per scene and mode for the life of the process; ~1 s the first time, outside the timed region).
+ * per scene, mode and render layout - one GPU or several, row blocks, sample runs - for the life of the process and on
+ * disk; ~0.5 s the first time, outside the timed region).
  * mode: 0 = never (generic kernel, scene in __constant__ memory); 1 (default; the environment variable PTB200_JIT
  * overrides the default) = renders of >= 2^25 paths wait for the build, smaller ones never wait: once they have
  * spent 300 ms of GPU time (PTB200_JIT_BG_MS) in the generic kernel the build of their (scene, mode) runs on a host

@@ -114,6 +114,7 @@ struct PtJitKernel {
 };
 // render_flags: PT_RF_* bits of the render the module is built for (regeneration branches as compile-time constants), -1 = none
 std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect = false, int render_flags = -1);
+int pt_jit_block(const SceneF32 &S);      // threads per block of the scene's specialised module
 int pt_jit_compile(const std::string &spec, std::vector<char> &cubin, std::string &log, double *seconds);
 PtJitKernel *pt_jit_get(pt_ctx *ctx, int mode, bool stats, bool with_intersect = false, bool wait = true, int render_flags = -1);
 void pt_jit_account(pt_ctx *ctx, int mode, bool stats, double ms, int render_flags = -1);

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -120,6 +121,15 @@ double background_after_ms()
 
 }  // namespace
 
+// Threads per block of a scene's specialised module (the host launches it with the same number): 512 for the scenes whose
+// warps iterate in lockstep over a long immediate sphere table (see PT_LOCKSTEP below), else the PT_BLOCK of the ahead-of-time build.
+int pt_jit_block(const SceneF32 &S)
+{
+    if (const char *e = std::getenv("PTB200_JIT_BLOCK")) return std::max(32, std::atoi(e));       // tuning aid, with -DPT_BLOCK=... in PTB200_JIT_OPTS
+    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX && !std::getenv("PTB200_NO_BLOCK512")) return 512;
+    return 256;
+}
+
 // The specialisation header of a scene: everything k_bounce reads through PT_SC / PT_J_SLOT.
 std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_intersect, int render_flags)
 {
@@ -202,7 +212,12 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     // Long immediate sphere tables make the kernel instruction-fetch bound (C4: `no_instruction` is the top stall, 4.4 per issue): the
     // warps of a block then iterate in lockstep (one block-wide barrier per bounce) and walk the straight-line scan together,
     // sharing instruction-cache lines: +9.5 % on C4 (-3 % on scene A, where it stays off).
-    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) h += "#ifndef PT_NO_LOCKSTEP\n#define PT_LOCKSTEP 1\n#endif\n";
+    // ... in blocks of 512 threads, so that 16 warps share the lines they fetch: another +6 % on C4 (1024: +3 %, 128: -8 %)
+    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {
+        char bl[128];
+        std::snprintf(bl, sizeof bl, "#ifndef PT_NO_LOCKSTEP\n#define PT_LOCKSTEP 1\n#ifndef PT_BLOCK\n#define PT_BLOCK %d\n#endif\n#endif\n", pt_jit_block(S));
+        h += bl;
+    }
     if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates
         std::snprintf(b, sizeof b, "#define PT_J_SPH_IMM %d\nconstexpr float PT_J_SPHF[%d][4] = {\n", PT_JIT_SPH_IMM_MAX, S.n_sph4);
         h += b;

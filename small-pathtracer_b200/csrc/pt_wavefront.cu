@@ -97,12 +97,10 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
-template <int MODE> void launch_bounce(bool stats, bool glossy, int blocks, cudaStream_t s, const KParams &P, const PtJitKernel *jk)
+template <int MODE> void launch_bounce(bool stats, bool glossy, int blocks, cudaStream_t s, const KParams &P, const PtJitKernel *jk, int jit_block)
 {
-    if (jk) {           // scene-specialised module (pt_jit.cu): same KParams, launched through its kernel handle
+    if (jk) {           // scene-specialised module (pt_jit.cu): same KParams, launched through its kernel handle with ITS block size
         void *args[] = {(void *)&P};
-        // (PTB200_JIT_BLOCK: tuning aid, the block size a module built with -DPT_BLOCK=... through PTB200_JIT_OPTS expects)
-        static const int jit_block = std::getenv("PTB200_JIT_BLOCK") ? std::max(32, std::atoi(std::getenv("PTB200_JIT_BLOCK"))) : PT_BLOCK;
         cudaLaunchKernel((const void *)jk->kern, dim3(blocks * PT_BLOCK / jit_block), dim3(jit_block), args, 0, s);
         return;
     }
@@ -326,6 +324,7 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
         P.spawn_slots = want_spawn ? PT_SPAWN_SLOTS : 0u;
 
         const int blocks = cap / PT_BLOCK;
+        const int jit_block = jk ? pt_jit_block(*ctx->h_scene32) : PT_BLOCK;
         const bool glossy = (ctx->h_scene32->refl_mask & ((1 << PT_SPEC) | (1 << PT_REFR))) != 0;
         unsigned int *n_it = ctx->d_counts + 4;
         // Termination check without draining the pipeline: batch k+1 is enqueued before the live count
@@ -344,10 +343,10 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
                 P.launch_rec = ctx->d_launch_rec + std::min(it, PT_MAX_LAUNCH_RECS - 1);
                 P.launch_rec0 = ctx->d_launch_rec;
                 switch (p->mode) {
-                case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, glossy, blocks, s, P, jk); break;
-                case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, glossy, blocks, s, P, jk); break;
-                case PT_MODE_UNI: launch_bounce<PT_MODE_UNI>(stats, glossy, blocks, s, P, jk); break;
-                default: launch_bounce<PT_MODE_NEE_CONE_SPHERE>(stats, glossy, blocks, s, P, jk); break;
+                case PT_MODE_NEE_REF_RECT: launch_bounce<PT_MODE_NEE_REF_RECT>(stats, glossy, blocks, s, P, jk, jit_block); break;
+                case PT_MODE_COS: launch_bounce<PT_MODE_COS>(stats, glossy, blocks, s, P, jk, jit_block); break;
+                case PT_MODE_UNI: launch_bounce<PT_MODE_UNI>(stats, glossy, blocks, s, P, jk, jit_block); break;
+                default: launch_bounce<PT_MODE_NEE_CONE_SPHERE>(stats, glossy, blocks, s, P, jk, jit_block); break;
                 }
                 ctx->stats.kernel_launches++;
             }
