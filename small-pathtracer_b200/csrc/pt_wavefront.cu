@@ -285,7 +285,10 @@ int pt_fp32_render(pt_ctx *ctx, const pt_render_params *p, double *d_sum, double
             unsigned long long c = total / ((unsigned long long)(cap / 32) * 2ull);
             unsigned int chunk = 32;
             while (chunk < 256 && chunk * 2ull <= c) chunk *= 2;
+            if (run_shift > 0) chunk = 32;          // (a run is dozens of paths: one per lane is plenty to reserve at a time)
             P.chunk = chunk;
+            // sample runs: reserve ahead only while more than this many runs are left (default: 3 per slot)
+            P.run_reserve = (unsigned long long)cap * (std::getenv("PTB200_RUN_RESERVE") ? (unsigned long long)std::max(0, std::atoi(std::getenv("PTB200_RUN_RESERVE"))) : 3ull);
             unsigned int sh = 0;
             while ((1ull << sh) < (unsigned long long)(cap / 32) / 2ull) sh++;     // fair share = remaining / (warps / 2)
             if (const char *e = std::getenv("PTB200_FAIR_DELTA")) { const int dlt = std::atoi(e); sh = (unsigned int)std::max(0, (int)sh + dlt); }
