@@ -302,9 +302,20 @@ int pt_set_acceleration(pt_ctx *ctx, int mode);
 int pt_debug_stats(pt_ctx *ctx, pt_stats *stats);
 
 /* Host-only (no device needed): the specialisation header generated for `scene` and render mode `mode`, and the
- * size of the sm_100a cubin NVRTC builds from it.  spec_out/cubin_bytes/seconds may be NULL. Test entry. */
+ * size of the sm_100a cubin NVRTC builds from it.  spec_out/cubin_bytes/seconds may be NULL.  Bits 8 and up of `mode`,
+ * when not zero, are 1 + the layout flags (pt_plan_info.layout_flags) of the render the module is for. Test entry. */
 int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t spec_cap, size_t *cubin_bytes,
                         double *seconds);
+
+/* Host-only (no device needed): how the FP32 engine would lay out a render of `scene` with `params` on a GPU of `sm_count`
+ * SMs - rows and pixels this rank owns, row blocks, path slots in flight, sample-run length (1 = single samples), path
+ * indices in total, and the layout flags a scene-specialised module is built for (bit 0: blocks of >= 32 pixels, 1: all
+ * index divisions by multiply-shift, 2: one GPU owns every row, 3: one row block, 4: sample runs).  Test entry. */
+typedef struct pt_plan_info {
+    uint64_t owned_rows, owned_pixels, row_blocks, block_rows, path_slots, run_length, path_indices;
+    uint32_t layout_flags, splits_refr_paths;
+} pt_plan_info;
+int pt_debug_plan(const pt_scene *scene, const pt_render_params *params, int sm_count, pt_plan_info *out);
 
 void        pt_destroy(pt_ctx *ctx);
 const char *pt_last_error(pt_ctx *ctx);   /* ctx may be NULL: last error of a failed upload */

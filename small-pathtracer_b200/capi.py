@@ -275,7 +275,7 @@ _lib = None
 LIB_PATH = os.path.join(HERE, "libptb200.so")
 EXPORTS = ["pt_scene_upload", "pt_render", "pt_render_multi", "pt_render_into", "pt_readback", "pt_readback_view", "pt_readback_owned", "pt_host_register", "pt_host_unregister", "pt_accum_device_ptr",
            "pt_debug_intersect", "pt_debug_erand48", "pt_debug_philox", "pt_debug_ffma_peak",
-           "pt_set_specialisation", "pt_set_acceleration", "pt_debug_specialise", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
+           "pt_set_specialisation", "pt_set_acceleration", "pt_debug_specialise", "pt_debug_plan", "pt_debug_stats", "pt_accum_upload", "pt_accum_download", "pt_device_alloc", "pt_device_free", "pt_ipc_export", "pt_ipc_open", "pt_ipc_close", "pt_destroy", "pt_last_error", "pt_version"]
 
 
 def lib():
@@ -335,11 +335,33 @@ def render_multi(contexts, p):
     contexts[0]._check(rc, "pt_render_multi")
 
 
-def specialise(scene, mode=PT_MODE_NEE_REF_RECT):
-    """Host-only: (specialisation header text, cubin bytes, NVRTC seconds) for `scene` — no GPU needed."""
+class PlanInfo(C.Structure):
+    _fields_ = [("owned_rows", C.c_uint64), ("owned_pixels", C.c_uint64), ("row_blocks", C.c_uint64), ("block_rows", C.c_uint64),
+                ("path_slots", C.c_uint64), ("run_length", C.c_uint64), ("path_indices", C.c_uint64),
+                ("layout_flags", C.c_uint32), ("splits_refr_paths", C.c_uint32)]
+
+
+def plan(scene, p, sm_count=148):
+    """Host-only: the FP32 engine's layout of a render (pt_debug_plan) - no GPU needed."""
+    d = scene.desc()
+    out = PlanInfo()
+    L = lib()
+    L.pt_debug_plan.argtypes = [C.POINTER(SceneDesc), C.POINTER(RenderParams), C.c_int, C.POINTER(PlanInfo)]
+    rc = L.pt_debug_plan(C.byref(d), C.byref(p), sm_count, C.byref(out))
+    if rc:
+        msg = L.pt_last_error(None)
+        raise PtError(f"pt_debug_plan failed ({rc}): {msg.decode() if msg else ''}")
+    return out
+
+
+def specialise(scene, mode=PT_MODE_NEE_REF_RECT, layout_flags=None):
+    """Host-only: (specialisation header text, cubin bytes, NVRTC seconds) for `scene` — no GPU needed.
+    layout_flags: PlanInfo.layout_flags of the render the module is for (None: a module for any layout)."""
     d = scene.desc()
     buf = C.create_string_buffer(1 << 16)
     nbytes, secs = C.c_size_t(0), C.c_double(0)
+    if layout_flags is not None:
+        mode = mode | ((layout_flags + 1) << 8)
     rc = lib().pt_debug_specialise(C.byref(d), mode, buf, len(buf), C.byref(nbytes), C.byref(secs))
     if rc:
         msg = lib().pt_last_error(None)

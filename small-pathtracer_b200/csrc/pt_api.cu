@@ -591,7 +591,8 @@ int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t 
     int rc = PT_OK;
     if (!tmp.fp32_ok) rc = pt_fail(nullptr, PT_ERR_ARG, "scene does not fit the FP32 engine: " + tmp.fp32_why);
     else {
-        const std::string spec = pt_jit_spec(*S, mode, false);
+        // (bits 8 and up of `mode`: layout flags + 1 of the render the module is for, 0 = none)
+        const std::string spec = pt_jit_spec(*S, mode & 0xFF, false, false, (mode >> 8) - 1);
         if (spec_out && spec_cap) { std::strncpy(spec_out, spec.c_str(), spec_cap - 1); spec_out[spec_cap - 1] = 0; }
         std::vector<char> cubin;
         std::string log;
@@ -602,6 +603,33 @@ int pt_debug_specialise(const pt_scene *scene, int mode, char *spec_out, size_t 
     tmp.h_scene32 = nullptr;
     delete S;
     return rc;
+}
+
+int pt_debug_plan(const pt_scene *scene, const pt_render_params *params, int sm_count, pt_plan_info *out)
+{
+    // host only: the scene's material mask as pt_scene_upload derives it, then the pure layout function of the FP32 engine
+    if (!scene || !params || !out || sm_count <= 0) return pt_fail(nullptr, PT_ERR_ARG, "null argument");
+    if (params->width <= 0 || params->height <= 0 || params->spp < 0 || params->width > 65535 || params->height > 65535)
+        return pt_fail(nullptr, PT_ERR_ARG, "bad render size");
+    pt_ctx tmp;
+    std::string why;
+    if (flatten_scene(scene, tmp.objs, why) != PT_OK) return pt_fail(nullptr, PT_ERR_ARG, why);
+    tmp.cam = scene->camera;
+    tmp.light = scene->light;
+    std::vector<MatF32> mats;
+    SceneF32 *S = new (std::nothrow) SceneF32;
+    if (!S) return pt_fail(nullptr, PT_ERR_OOM, "host allocation failed");
+    tmp.h_scene32 = S;
+    build_scene_f32(&tmp, mats);
+    tmp.sm_count = sm_count;
+    Fp32Plan pl;
+    pt_fp32_plan(&tmp, params, pl);
+    out->owned_rows = (uint64_t)pl.owned_rows; out->owned_pixels = pl.owned_pixels; out->row_blocks = pl.n_blk; out->block_rows = pl.blk_rows;
+    out->path_slots = (uint64_t)pl.cap; out->run_length = 1ull << pl.run_shift; out->path_indices = pl.total;
+    out->layout_flags = (uint32_t)pl.flags; out->splits_refr_paths = pl.want_spawn ? 1u : 0u;
+    tmp.h_scene32 = nullptr;
+    delete S;
+    return PT_OK;
 }
 
 int pt_render_into(pt_ctx *ctx, const pt_render_params *p, void *dev_rgb_sum, void *stream)

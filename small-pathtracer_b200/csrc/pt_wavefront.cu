@@ -164,15 +164,15 @@ void pt_fp32_plan(const pt_ctx *ctx, const pt_render_params *p, Fp32Plan &pl)
     pl.cap = (cap + 1023) / 1024 * 1024;              // whole blocks for any block size up to 1024
     // REFR path splitting (:494-495): per-warp stacks of spawned branches, only for scenes that have such a material
     pl.want_spawn = ((ctx->h_scene32->refl_mask >> PT_REFR) & 1) && !stats && !std::getenv("PTB200_NO_SPLIT");
-    // Sample runs (KParams::run_shift): 64 or 128 consecutive samples of a pixel per path index when a slot traces at least
-    // 64 runs in this render, else single samples.  A render of runs ends with every slot finishing a run of its own
-    // (~1-2 % of a render that size; shorter runs end so often that some lane of a warp needs the chunk step in most
-    // iterations anyway: measured, a loss below 64).  A lane that takes over spawned REFR branches has no run of its
-    // own to come back to, so those scenes keep single samples too.
+    // Sample runs (KParams::run_shift): 128 consecutive samples of a pixel per path index when a slot traces at least 2048
+    // paths in this render, else single samples (measured on shares of C5: at 2336 paths per slot runs of 128 gain 3 %, at
+    // 1168 runs of 64 gain 0.8 % on one GPU and lose as much in the 8-GPU step, runs of 32 nothing; on C2's 147 paths per
+    // slot runs of 16 lose 10 %: a render of runs ends with every slot finishing the run it is in, and shorter runs end so
+    // often that some lane of a warp needs the chunk step in most iterations anyway).  A lane that takes over spawned REFR
+    // branches has no run of its own to come back to, so those scenes keep single samples too.
     {
         const unsigned long long per_slot = pl.owned_pixels * (unsigned long long)p->spp / (unsigned long long)pl.cap;
-        unsigned long long run = std::min<unsigned long long>(128ull, per_slot / 64ull);
-        if (run < 64ull) run = 1;
+        unsigned long long run = per_slot >= 2048ull ? 128ull : 1ull;
         if (const char *e = std::getenv("PTB200_RUN")) run = (unsigned long long)std::max(1ll, std::atoll(e));
         if (pl.want_spawn) run = 1;
         while ((2ull << pl.run_shift) <= run && (2ull << pl.run_shift) <= (unsigned long long)p->spp && pl.run_shift < 12) pl.run_shift++;

@@ -49,6 +49,39 @@ def test_header_carries_the_scene_constants():
 
 
 @pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+def test_module_for_a_render_layout_and_shadow_rays_without_slot_codes():
+    # a module is built for the render's layout flags (pt_plan_info.layout_flags): the regeneration step then tests nothing
+    # of it at run time.  C5's layout: blocks of >= 32 pixels, multiply-shift divisions, one GPU, row blocks, sample runs.
+    sc = ptb.builtin_scene("A", 3840, 2160)
+    flags = ptb.plan(sc, ptb.params(3840, 2160, 1024, mode=0)).layout_flags
+    spec, cubin_bytes, _ = ptb.specialise(sc, 0, flags)
+    for line in ("#define PT_BAKE_WORLD1 1", "#define PT_BAKE_RUNS 1", "#define PT_BAKE_WRAP_ONCE 1", "#define PT_BAKE_MAGIC 1"):
+        assert line in spec
+    assert "PT_NO_ROW_BLOCKS" not in spec and cubin_bytes > 10000
+    small = ptb.specialise(sc, 0, ptb.plan(sc, ptb.params(512, 512, 512, mode=0)).layout_flags)[0]
+    assert "#define PT_BAKE_RUNS 0" in small and "#define PT_NO_ROW_BLOCKS 1" in small
+    eighth = ptb.specialise(sc, 0, ptb.plan(sc, ptb.params(3840, 2160, 1024, mode=0, tile_rows=10, rank=3, world=8)).layout_flags)[0]
+    assert "#define PT_BAKE_WORLD1 0" in eighth and "#define PT_BAKE_RUNS 0" in eighth
+    assert "PT_BAKE_" not in ptb.specialise(sc, 0)[0]                      # no layout given: everything stays a run-time test
+    # shadow rays toward the rectangular light compete without slot codes only when no other rectangle comes near the light's
+    # (scene A: the ceiling is 0.1 away, plenty) and only in the reference's NEE mode
+    assert "#define PT_J_SHADOW_RAW 1" in spec and "PT_J_SHADOW_RAW" not in ptb.specialise(sc, 1)[0]
+    near = ptb.builtin_scene("A", 64, 64)
+    rects = list(near.planes)
+    rects.append(ptb.rect(ptb.PT_PLANE_XZ, 40, 60, 70, 90, 81.5005, c=(.5, .5, .5)))     # a rectangle 5e-4 above the light
+    crowded = ptb.Scene([], rects, list(range(len(rects))), near.light, near.camera)
+    assert "PT_J_SHADOW_RAW" not in ptb.specialise(crowded, 0)[0]
+
+
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+def test_lockstep_modules_use_512_thread_blocks():
+    # long immediate sphere tables are instruction-fetch bound: block-wide lockstep, 512 threads per block
+    spec = ptb.specialise(ptb.builtin_scene("synthetic", 64, 64), 1)[0]
+    assert "#define PT_LOCKSTEP 1" in spec and "#define PT_BLOCK 512" in spec
+    assert "PT_LOCKSTEP" not in ptb.specialise(ptb.builtin_scene("A", 64, 64), 1)[0]
+
+
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
 def test_disk_cache_serves_the_second_process(tmp_path):
     import os, subprocess, sys
     from conftest import ROOT
