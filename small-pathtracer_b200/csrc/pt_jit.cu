@@ -121,13 +121,15 @@ double background_after_ms()
 
 }  // namespace
 
-// Threads per block of a scene's specialised module (the host launches it with the same number): 512 for the scenes whose
-// warps iterate in lockstep over a long immediate sphere table (see PT_LOCKSTEP below), else the PT_BLOCK of the ahead-of-time build.
+// Threads per block of a scene's specialised module (the host launches it with the same number).  One block of 1024 threads
+// per SM measured 1.7-5 % faster than four of 256 on every config (C5 263.1 -> 255.4 ms, C2 4.89 -> 4.81, C3 1.66 -> 1.60,
+// an eighth of C5 35.8 -> 34.85; 128 or 64 threads: 0.7 % slower); the scenes whose warps iterate in lockstep over a long
+// immediate sphere table (PT_LOCKSTEP below) do best with 512 (C4 561.6 -> 530.0 ms; 1024: 544).
 int pt_jit_block(const SceneF32 &S)
 {
     if (const char *e = std::getenv("PTB200_JIT_BLOCK")) return std::max(32, std::atoi(e));       // tuning aid, with -DPT_BLOCK=... in PTB200_JIT_OPTS
-    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX && !std::getenv("PTB200_NO_BLOCK512")) return 512;
-    return 256;
+    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) return 512;
+    return 1024;
 }
 
 // The specialisation header of a scene: everything k_bounce reads through PT_SC / PT_J_SLOT.
@@ -213,9 +215,10 @@ std::string pt_jit_spec(const SceneF32 &S, int mode, bool stats, bool with_inter
     // warps of a block then iterate in lockstep (one block-wide barrier per bounce) and walk the straight-line scan together,
     // sharing instruction-cache lines: +9.5 % on C4 (-3 % on scene A, where it stays off).
     // ... in blocks of 512 threads, so that 16 warps share the lines they fetch: another +6 % on C4 (1024: +3 %, 128: -8 %)
-    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {
-        char bl[128];
-        std::snprintf(bl, sizeof bl, "#ifndef PT_NO_LOCKSTEP\n#define PT_LOCKSTEP 1\n#ifndef PT_BLOCK\n#define PT_BLOCK %d\n#endif\n#endif\n", pt_jit_block(S));
+    if (S.n_sph4 >= 64 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) h += "#ifndef PT_NO_LOCKSTEP\n#define PT_LOCKSTEP 1\n#endif\n";
+    {
+        char bl[96];
+        std::snprintf(bl, sizeof bl, "#ifndef PT_BLOCK\n#define PT_BLOCK %d\n#endif\n", pt_jit_block(S));      // threads per block of this module
         h += bl;
     }
     if (S.n_sph4 > 0 && S.n_sph4 <= PT_JIT_SPH_IMM_MAX) {      // small sphere sets: the scan table as immediates

@@ -78,7 +78,8 @@ def test_lockstep_modules_use_512_thread_blocks():
     # long immediate sphere tables are instruction-fetch bound: block-wide lockstep, 512 threads per block
     spec = ptb.specialise(ptb.builtin_scene("synthetic", 64, 64), 1)[0]
     assert "#define PT_LOCKSTEP 1" in spec and "#define PT_BLOCK 512" in spec
-    assert "PT_LOCKSTEP" not in ptb.specialise(ptb.builtin_scene("A", 64, 64), 1)[0]
+    other = ptb.specialise(ptb.builtin_scene("A", 64, 64), 1)[0]
+    assert "PT_LOCKSTEP" not in other and "#define PT_BLOCK 1024" in other          # everything else: one block of 1024 threads per SM
 
 
 @pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
