@@ -122,7 +122,7 @@ double background_after_ms()
 }  // namespace
 
 // Threads per block of a scene's specialised module (the host launches it with the same number).  One block of 1024 threads
-// per SM measured 1.7-5 % faster than four of 256 on every config (C5 263.1 -> 255.4 ms, C2 4.89 -> 4.81, C3 1.66 -> 1.60,
+// per SM (also the ahead-of-time build's: C2 9.02 -> 8.20 ms there) measured 1.7-5 % faster than four of 256 on every config (C5 263.1 -> 255.4 ms, C2 4.89 -> 4.81, C3 1.66 -> 1.60,
 // an eighth of C5 35.8 -> 34.85; 128 or 64 threads: 0.7 % slower); the scenes whose warps iterate in lockstep over a long
 // immediate sphere table (PT_LOCKSTEP below) do best with 512 (C4 561.6 -> 530.0 ms; 1024: 544).
 int pt_jit_block(const SceneF32 &S)
