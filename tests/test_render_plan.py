@@ -91,6 +91,26 @@ def test_other_gpus_scale_the_slots():
     assert plan("A", 3840, 2160, 1024, mode=0, queue_capacity=5000).path_slots == 5120
 
 
+def test_library_and_python_plumbing_agree_on_row_ownership():
+    # tile k -> rank k % world: the library's count of owned rows equals dist.owned_rows (what gather_rows, HostImage and the
+    # tests use to place a rank's rows) for ragged heights, odd tiles and ranks without rows
+    from small_pathtracer_b200 import dist as pdist
+    import random
+    rng = random.Random(5)
+    for _ in range(60):
+        h, w = rng.randint(1, 400), rng.randint(1, 64)
+        tile, world = rng.randint(1, 17), rng.randint(1, 9)
+        total = 0
+        for rank in range(world):
+            pl = plan("A", w, h, 2, mode=1, tile_rows=tile, rank=rank, world=world)
+            rows = pdist.owned_rows(h, tile, rank, world)
+            assert pl.owned_rows == len(rows) and pl.owned_pixels == len(rows) * w
+            if len(rows):
+                assert all(((int(y) // tile) % world) == rank for y in rows)
+            total += pl.owned_rows
+        assert total == h
+
+
 def test_bad_arguments():
     with pytest.raises(ptb.PtError):
         ptb.plan(ptb.builtin_scene("A", 8, 8), ptb.params(0, 8, 1), 148)
