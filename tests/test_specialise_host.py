@@ -74,6 +74,21 @@ def test_module_for_a_render_layout_and_shadow_rays_without_slot_codes():
 
 
 @pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
+def test_every_layout_flag_combination_compiles():
+    # a module that failed to build would silently leave the render on the generic kernel: every combination of the five
+    # layout flags must compile for sm_100a (scene A in the reference's NEE mode; the glass scene and the 256-sphere scene with
+    # cone sampling - the lockstep / called-closest_hit variants - for the combinations a render can actually have)
+    sc = ptb.builtin_scene("A", 64, 64)
+    for flags in range(32):
+        spec, cubin_bytes, _ = ptb.specialise(sc, 0, flags)
+        assert cubin_bytes > 10000, flags
+        assert ("#define PT_BAKE_RUNS 1" in spec) == bool(flags & 16) and ("#define PT_NO_ROW_BLOCKS 1" in spec) == bool(flags & 8)
+    for scene, mode in (("G", 1), ("synthetic", 3), ("B", 3)):
+        for flags in (1 | 2 | 4 | 8, 1 | 2, 1 | 2 | 4 | 16, 4):
+            assert ptb.specialise(ptb.builtin_scene(scene, 64, 64), mode, flags)[1] > 10000, (scene, mode, flags)
+
+
+@pytest.mark.skipif(not _have_nvrtc(), reason="libnvrtc not installed")
 def test_lockstep_modules_use_512_thread_blocks():
     # long immediate sphere tables are instruction-fetch bound: block-wide lockstep, 512 threads per block
     spec = ptb.specialise(ptb.builtin_scene("synthetic", 64, 64), 1)[0]
